@@ -1,0 +1,175 @@
+/*
+ * mvoc_b200.h — C-ABI of the B200-native MVOC composition hot path.
+ *
+ * Every entry point takes raw device pointers, explicit shapes/strides and a
+ * cudaStream_t (passed as void*).  No call allocates, synchronises or falls
+ * back to another implementation: an unsupported shape/dtype returns a
+ * negative error code and the text is available from mvoc_last_error().
+ * sm_100a only.
+ *
+ * Each function cites the reference interface it replaces (paths relative to
+ * the SobeyMIL/MVOC tree).  The reference is Python on diffusers; the
+ * binding a maintainer would add is a ctypes stub — see INTEGRATION.md.
+ *
+ * Batch-slot convention (i2vgen-xl/pipelines/pipeline_i2vgen_xl.py:1675-1677):
+ *   slot 0 = background, slots 1..n_obj = objects, slot n_obj+1 = uncond
+ *   composite, slot n_obj+2 = cond composite.  n_branches = n_obj + 3.
+ */
+#ifndef MVOC_B200_H
+#define MVOC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVOC_MAX_OBJECTS 8
+
+/* return codes */
+#define MVOC_OK 0
+#define MVOC_ERR_INVALID_ARG (-1)
+#define MVOC_ERR_UNSUPPORTED (-2)
+#define MVOC_ERR_CUDA (-3)
+#define MVOC_ERR_DRIVER (-4)
+
+/* storage dtypes */
+#define MVOC_BF16 0
+#define MVOC_F16 1
+#define MVOC_F32 2
+
+/* mask kinds for the blends */
+#define MVOC_MASK_U8 0  /* binary select, bit exact  */
+#define MVOC_MASK_F32 1 /* soft mask, fp32 lerp, rounded once */
+
+const char* mvoc_version(void);
+const char* mvoc_last_error(void);
+/* 0 if `device` is compute capability 10.x, MVOC_ERR_UNSUPPORTED otherwise. */
+int mvoc_device_check(int device);
+
+/*
+ * Dense non-causal attention forward, O = softmax(Q K^T * scale) V.
+ * Replaces F.scaled_dot_product_attention at i2vgen-xl/pnp_utils.py:684-686
+ * (injected spatial attn1) and the same call inside diffusers'
+ * AttnProcessor2_0 for every spatial self-attention and cross-attention
+ * (reached through attention_forward, i2vgen-xl/pnp_utils.py:348-385).
+ *
+ * q,o: [B, Nq, H, D]   k,v: [B, Nk, H, D]   D innermost and contiguous, D == 64.
+ * Strides are in ELEMENTS for (batch, token, head).  Tensor-core path
+ * (tcgen05.mma, accumulators in TMEM, operands staged by TMA); bf16 only.
+ * Requirements: base pointers 16-byte aligned, strides multiples of 8.
+ * variant: 0 = default, 1 = force P-through-shared-memory (SS MMA),
+ *          2 = force P-in-TMEM (TS MMA).  Same results; used by the tests.
+ */
+int mvoc_attn_fwd(const void* q, const void* k, const void* v, void* o,
+                  int B, int H, int Nq, int Nk, int D,
+                  int64_t q_sb, int64_t q_sn, int64_t q_sh,
+                  int64_t k_sb, int64_t k_sn, int64_t k_sh,
+                  int64_t v_sb, int64_t v_sn, int64_t v_sh,
+                  int64_t o_sb, int64_t o_sn, int64_t o_sh,
+                  float scale, int dtype, int variant, void* stream);
+
+/*
+ * Short-sequence attention (tokens = frames), one warp per (pixel, head).
+ * Replaces F.scaled_dot_product_attention at i2vgen-xl/pnp_utils.py:862-864
+ * (injected temporal attn1) and the stock processor on the temporal attn2,
+ * transformer_in (i2vgen-xl/pnp_utils.py:170-220 drives them).
+ *
+ * q,k,v,o: [P, T, H, D], D == 64 contiguous, T in {8, 16, 24, 32};
+ * strides in elements for (problem, token, head).  HBM-bound; bf16 only.
+ */
+int mvoc_attn_temporal_fwd(const void* q, const void* k, const void* v, void* o,
+                           int64_t P, int T, int H, int D,
+                           int64_t q_sp, int64_t q_st, int64_t q_sh,
+                           int64_t k_sp, int64_t k_st, int64_t k_sh,
+                           int64_t v_sp, int64_t v_st, int64_t v_sh,
+                           int64_t o_sp, int64_t o_st, int64_t o_sh,
+                           float scale, int dtype, void* stream);
+
+/*
+ * Q/K mask-blend injection, in place.
+ * Replaces i2vgen-xl/pnp_utils.py:628-672 (spatial, binary mask) and
+ * :782-850 (temporal, float mask).
+ *
+ * x0, x1 (x1 may be NULL): [n_branches, tokens, C] contiguous — Q and K of one
+ * layer viewed with the branch slot outermost (spatial: tokens = T*h*w in
+ * (frame, pixel) order; temporal: tokens = h*w*T in (pixel, frame) order).
+ * mask: [n_obj, tokens] in the SAME token order, u8 (MVOC_MASK_U8: nonzero
+ * selects the object) or f32 (MVOC_MASK_F32: base*(1-m)+obj*m in fp32).
+ * base_slot: n_obj+2 (cond; inject_background False) or 0 (background).
+ * Result is written to slots n_obj+1 and n_obj+2.  C % 8 == 0.
+ */
+int mvoc_qk_blend(void* x0, void* x1, int n_obj, int64_t tokens, int C,
+                  const void* mask, int mask_kind, int base_slot,
+                  int dtype, void* stream);
+
+/*
+ * Hidden-state mask-blend after resnet conv2 / temporal conv / conv_out.
+ * Replaces i2vgen-xl/pnp_utils.py:970-1004, :1059-1082, :1114-1146.
+ *
+ * x: [n_branches*T, C, HW] contiguous (NCHW, frames fastest inside a slot),
+ * mask: [n_obj, T, HW] u8 (binary at full latent resolution).  base = slot 0
+ * always; result written to slots n_obj+1 and n_obj+2 in place.  Bit exact.
+ */
+int mvoc_feature_blend(void* x, int n_obj, int T, int C, int64_t HW,
+                       const void* mask, int dtype, void* stream);
+
+/*
+ * GroupNorm (+ optional SiLU) over [N, C, S] with G groups; statistics are
+ * shared by `frames_per_stat` consecutive n (1 = spatial GroupNorm on
+ * [B*T,C,H,W]; T = the 5-D GroupNorm on [B,C,T,H,W] stored frame-major).
+ * Replaces norm1/norm2 + nonlinearity at i2vgen-xl/pnp_utils.py:909-910,
+ * :953-965, the GN→SiLU heads of TemporalConvLayer.conv1..4 (:1048-1051),
+ * Transformer2DModel.norm (:430), TransformerTemporalModel.norm (:185-188) and
+ * conv_norm_out + conv_act (pipelines/pipeline_i2vgen_xl.py:351-352).
+ *
+ * gamma/beta: [C] in `dtype`.  y may alias x.  workspace: at least
+ * mvoc_groupnorm_workspace_bytes(N, G) bytes of device memory.
+ */
+int64_t mvoc_groupnorm_workspace_bytes(int64_t N, int G);
+int mvoc_groupnorm_silu(const void* x, void* y, const void* gamma, const void* beta,
+                        int64_t N, int C, int64_t S, int G, int frames_per_stat,
+                        float eps, int silu, int dtype, void* workspace, void* stream);
+
+/*
+ * Latent compositing ("noise fusion") fused with the UNet input concat.
+ * Replaces pipelines/pipeline_i2vgen_xl.py:1644-1663 and the torch.cat at
+ * :1675-1677.
+ *
+ * z [E] (in/out, E = 4*T*h*w laid out [4,T,h,w]), bg [E], objs [n_obj,E],
+ * mask [n_obj, T*h*w] f32 (broadcast over the 4 channels).
+ * do_fusion: z = r*z + (1-r)*bg; then per object
+ *   z = z*(1-M) + obj*M                       (obj_noise_fusion == 0)
+ *   z = z*(1-M) + r*z*M + (1-r)*obj*M         (obj_noise_fusion != 0)
+ * unet_in (nullable): [n_obj+3, E] receives [bg, objs..., z, z] in
+ * `in_dtype`; latents themselves are `lat_dtype`.
+ */
+int mvoc_latent_composite(void* z, const void* bg, const void* objs, const void* mask,
+                          void* unet_in, int n_obj, int64_t E, int64_t THW,
+                          float ratio, int do_fusion, int obj_noise_fusion,
+                          int lat_dtype, int in_dtype, void* stream);
+
+/*
+ * Classifier-free guidance + v-prediction DDIM update (eta = 0).
+ * Replaces pipelines/pipeline_i2vgen_xl.py:1713-1731 and diffusers
+ * DDIMScheduler.step.   v = u + g*(c-u);
+ *   x0 = sqrt(a_t) x - sqrt(1-a_t) v;  eps = sqrt(a_t) v + sqrt(1-a_t) x;
+ *   x_prev = sqrt(a_prev) x0 + sqrt(1-a_prev) eps.
+ * pred_cond may be NULL (no guidance: v = pred_uncond).
+ */
+int mvoc_cfg_ddim_step(const void* pred_uncond, const void* pred_cond, void* x,
+                       int64_t E, float guidance, double alpha_t, double alpha_prev,
+                       int pred_dtype, int lat_dtype, void* stream);
+
+/*
+ * Inverse DDIM step (pipelines/pipeline_i2vgen_xl.py:1967-1984 and diffusers
+ * DDIMInverseScheduler.step): same algebra, from level alpha_src to alpha_dst.
+ */
+int mvoc_ddim_inverse_step(const void* pred_uncond, const void* pred_cond, void* x,
+                           int64_t E, float guidance, double alpha_src, double alpha_dst,
+                           int pred_dtype, int lat_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVOC_B200_H */

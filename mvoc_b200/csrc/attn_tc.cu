@@ -1,0 +1,417 @@
+// Tensor-core flash attention forward for sm_100a (tcgen05 + TMEM + TMA).
+// Reference: F.scaled_dot_product_attention at i2vgen-xl/pnp_utils.py:684-686
+// and inside diffusers' AttnProcessor2_0 (reached through attention_forward,
+// i2vgen-xl/pnp_utils.py:348-385) — non-causal, no mask, no dropout, D = 64.
+//
+// One CTA = one 128-row query tile of one (batch, head); two CTAs per SM.
+//   warps 0-3  softmax: thread i owns query row i (= TMEM lane i), so row
+//              max / row sum need no shuffles
+//   warp  4    TMA producer: Q once, then a ring of K / V tiles
+//   warp  5    MMA issuer (one lane): S = Q K^T, O += P V; owns the TMEM allocation
+// TMEM columns (fp32): S [0,128)  P [128,192) (bf16 pairs)  O [192,256).
+// Q, K, V are read straight from the projection output [B, N, H*64] through
+// 4-D tensor maps (128-byte swizzle), so no head transpose is ever materialised.
+#include <cuda.h>
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mvoc {
+namespace attn {
+
+constexpr int BM = 128;  // query rows per CTA
+constexpr int BN = 128;  // keys per iteration
+constexpr int HD = 64;   // head dim
+constexpr int TILE_BYTES = BM * HD * 2;  // 16 KB: 128 rows x 128 B
+constexpr int THREADS = 192;
+constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192;
+constexpr float RESCALE_LOG2_THRESHOLD = 8.0f;
+
+template <bool kPInTmem, int kStages>
+struct Smem {
+    static constexpr int q_off = 0;
+    static constexpr int k_off = TILE_BYTES;
+    static constexpr int v_off = k_off + kStages * TILE_BYTES;
+    static constexpr int p_off = v_off + kStages * TILE_BYTES;
+    static constexpr int bar_off = p_off + (kPInTmem ? 0 : 2 * TILE_BYTES);
+    // barriers: q_full, s_full, s_free, p_full, pv_done, k_full[], k_empty[], v_full[], v_empty[]
+    static constexpr int n_bars = 5 + 4 * kStages;
+    static constexpr int tmem_ptr_off = bar_off + n_bars * 8;
+    static constexpr int total = tmem_ptr_off + 16;
+    static constexpr int alloc = total + 1024;  // slack to align the base to 1024 B
+};
+
+struct Params {
+    __nv_bfloat16* o;
+    int64_t o_sb, o_sn, o_sh;
+    int Nq, Nk;
+    float scale_log2;
+};
+
+template <bool kPInTmem, int kStages>
+__global__ void __launch_bounds__(THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const Params prm) {
+    using L = Smem<kPInTmem, kStages>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+
+    const uint32_t sQ = sbase + L::q_off;
+    const uint32_t sK = sbase + L::k_off;
+    const uint32_t sV = sbase + L::v_off;
+    const uint32_t sP = sbase + L::p_off;
+    const uint32_t bars = sbase + L::bar_off;
+    const uint32_t b_q_full = bars, b_s_full = bars + 8, b_s_free = bars + 16, b_p_full = bars + 24,
+                   b_pv_done = bars + 32;
+    const uint32_t b_k_full = bars + 40, b_k_empty = b_k_full + 8 * kStages,
+                   b_v_full = b_k_empty + 8 * kStages, b_v_empty = b_v_full + 8 * kStages;
+    const uint32_t s_tmem_ptr = sbase + L::tmem_ptr_off;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_blk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int n_blocks = (prm.Nk + BN - 1) / BN;
+
+    if (warp == 4 && lane == 0) {
+        ptx::prefetch_tensormap(&tm_q);
+        ptx::prefetch_tensormap(&tm_k);
+        ptx::prefetch_tensormap(&tm_v);
+        ptx::mbar_init(b_q_full, 1);
+        ptx::mbar_init(b_s_full, 1);
+        ptx::mbar_init(b_s_free, 128);
+        ptx::mbar_init(b_p_full, 128);
+        ptx::mbar_init(b_pv_done, 1);
+        for (int s = 0; s < kStages; ++s) {
+            ptx::mbar_init(b_k_full + 8 * s, 1);
+            ptx::mbar_init(b_k_empty + 8 * s, 1);
+            ptx::mbar_init(b_v_full + 8 * s, 1);
+            ptx::mbar_init(b_v_empty + 8 * s, 1);
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 5) {
+        ptx::tmem_alloc(s_tmem_ptr, TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + L::tmem_ptr_off);
+
+    if (warp == 4) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            ptx::mbar_expect_tx(b_q_full, TILE_BYTES);
+            ptx::tma_load_4d(sQ, &tm_q, b_q_full, 0, h, m_blk * BM, b);
+        }
+        for (int j = 0; j < n_blocks; ++j) {
+            const int s = j % kStages;
+            const uint32_t ph = (uint32_t)(j / kStages) & 1u;
+            ptx::mbar_wait(b_k_empty + 8 * s, ph ^ 1u, 1);
+            if (lane == 0) {
+                ptx::mbar_expect_tx(b_k_full + 8 * s, TILE_BYTES);
+                ptx::tma_load_4d(sK + s * TILE_BYTES, &tm_k, b_k_full + 8 * s, 0, h, j * BN, b);
+            }
+            ptx::mbar_wait(b_v_empty + 8 * s, ph ^ 1u, 2);
+            if (lane == 0) {
+                ptx::mbar_expect_tx(b_v_full + 8 * s, TILE_BYTES);
+                ptx::tma_load_4d(sV + s * TILE_BYTES, &tm_v, b_v_full + 8 * s, 0, h, j * BN, b);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 5) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t IDESC_QK = ptx::idesc_bf16(BM, BN, 0, 0);  // A,B K-major
+        constexpr uint32_t IDESC_PV = ptx::idesc_bf16(BM, HD, 0, 1);  // B (=V) MN-major
+        const uint32_t tS = tmem + COL_S, tP = tmem + COL_P, tO = tmem + COL_O;
+        auto issue_qk = [&](int j) {
+            const int s = j % kStages;
+            const uint64_t a0 = ptx::smem_desc_sw128(sQ, 16, 1024);
+            const uint64_t b0 = ptx::smem_desc_sw128(sK + s * TILE_BYTES, 16, 1024);
+#pragma unroll
+            for (int ks = 0; ks < HD / 16; ++ks)  // +32 B per 16-element K step (encoded >>4)
+                ptx::mma_ss(tS, a0 + (uint64_t)(ks * 2), b0 + (uint64_t)(ks * 2), IDESC_QK, ks > 0);
+            ptx::tc_commit(b_k_empty + 8 * s);
+            ptx::tc_commit(b_s_full);
+        };
+        ptx::mbar_wait(b_q_full, 0, 3);
+        ptx::mbar_wait(b_k_full, 0, 4);
+        ptx::tc_fence_after();
+        if (lane == 0) issue_qk(0);
+        __syncwarp();
+        for (int j = 0; j < n_blocks; ++j) {
+            const int s = j % kStages;
+            const uint32_t ph = (uint32_t)(j / kStages) & 1u;
+            if (j + 1 < n_blocks) {
+                const int s1 = (j + 1) % kStages;
+                ptx::mbar_wait(b_k_full + 8 * s1, (uint32_t)((j + 1) / kStages) & 1u, 5);
+                ptx::mbar_wait(b_s_free, (uint32_t)j & 1u, 6);
+                ptx::tc_fence_after();
+                if (lane == 0) issue_qk(j + 1);
+                __syncwarp();
+            }
+            ptx::mbar_wait(b_v_full + 8 * s, ph, 7);
+            ptx::mbar_wait(b_p_full, (uint32_t)j & 1u, 8);
+            ptx::tc_fence_after();
+            if (lane == 0) {
+                // V tile: rows = keys (K of this GEMM), 128 B per row = 64 d (N) contiguous
+                const uint64_t bv = ptx::smem_desc_sw128(sV + s * TILE_BYTES, 16384, 1024);
+#pragma unroll
+                for (int ks = 0; ks < BN / 16; ++ks) {
+                    const uint64_t bd = bv + (uint64_t)((ks * 2048) >> 4);
+                    const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+                    if (kPInTmem) {
+                        ptx::mma_ts(tO, tP + ks * 8, bd, IDESC_PV, acc);
+                    } else {
+                        const uint64_t ap = ptx::smem_desc_sw128(
+                            sP + (ks >> 2) * TILE_BYTES + (ks & 3) * 32, 16, 1024);
+                        ptx::mma_ss(tO, ap, bd, IDESC_PV, acc);
+                    }
+                }
+                ptx::tc_commit(b_v_empty + 8 * s);
+                ptx::tc_commit(b_pv_done);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== softmax + epilogue (warps 0-3) =====================
+        const int row = threadIdx.x;  // query row inside the tile == TMEM lane
+        const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t tS = lane_base + COL_S, tP = lane_base + COL_P, tO = lane_base + COL_O;
+        const float sl2 = prm.scale_log2;
+        float m_used = -INFINITY, l_sum = 0.0f;
+        for (int j = 0; j < n_blocks; ++j) {
+            const int valid = min(BN, prm.Nk - j * BN);
+            const bool tail = valid < BN;
+            ptx::mbar_wait(b_s_full, (uint32_t)j & 1u, 9);
+            ptx::tc_fence_after();
+            // pass 1: row max
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                ptx::tmem_ld32(tS + c * 32, r);
+                ptx::tmem_wait_ld();
+                if (tail) {  // keys past Nk (zero-filled by TMA) must not take part
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i >= valid) r[i] = 0xff800000u;  // -inf
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+            }
+            bool pv_waited = false;
+            if (j == 0) {
+                m_used = mx;
+            } else {
+                const float m_new = fmaxf(m_used, mx);
+                const bool need = (m_new - m_used) * sl2 > RESCALE_LOG2_THRESHOLD;
+                if (__any_sync(0xffffffffu, need)) {
+                    // rescale the running O and l (rare after the first blocks)
+                    ptx::mbar_wait(b_pv_done, (uint32_t)(j - 1) & 1u, 10);
+                    ptx::tc_fence_after();
+                    pv_waited = true;
+                    const float f = need ? ptx::ex2_approx((m_used - m_new) * sl2) : 1.0f;
+                    if (need) m_used = m_new;
+                    l_sum *= f;
+#pragma unroll
+                    for (int c = 0; c < HD / 32; ++c) {
+                        uint32_t r[32];
+                        ptx::tmem_ld32(tO + c * 32, r);
+                        ptx::tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+                        ptx::tmem_st32(tO + c * 32, r);
+                    }
+                    ptx::tmem_wait_st();
+                }
+            }
+            // pass 2: p = exp2((s - m) * scale*log2e), packed to bf16 pairs
+            const float neg_m = -m_used * sl2;
+            uint32_t pk[BN / 2];
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                ptx::tmem_ld32(tS + c * 32, r);
+                ptx::tmem_wait_ld();
+                if (tail) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i >= valid) r[i] = 0xff800000u;  // exp2(-inf) = 0
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(r[i]), sl2, neg_m));
+                    const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 1]), sl2, neg_m));
+                    l_sum += p0 + p1;
+                    __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                    pk[c * 16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&pb);
+                }
+            }
+            // S has been consumed: let the MMA warp overwrite it with the next Q K^T
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(b_s_free);
+            // P buffer is free once the previous P V has completed
+            if (j > 0 && !pv_waited) {
+                ptx::mbar_wait(b_pv_done, (uint32_t)(j - 1) & 1u, 11);
+                ptx::tc_fence_after();
+            }
+            if (kPInTmem) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t r[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = pk[c * 32 + i];
+                    ptx::tmem_st32(tP + c * 32, r);
+                }
+                ptx::tmem_wait_st();
+                ptx::tc_fence_before();
+            } else {
+                // row `row` of two K-major 128B-swizzled tiles (keys 0-63, 64-127)
+#pragma unroll
+                for (int cc = 0; cc < 16; ++cc) {
+                    const uint32_t addr = sP + (cc >> 3) * TILE_BYTES + row * 128 +
+                                          (((cc & 7) ^ (row & 7)) << 4);
+                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr),
+                                 "r"(pk[cc * 4]), "r"(pk[cc * 4 + 1]), "r"(pk[cc * 4 + 2]),
+                                 "r"(pk[cc * 4 + 3])
+                                 : "memory");
+                }
+                ptx::fence_proxy_async_smem();
+            }
+            ptx::mbar_arrive(b_p_full);
+        }
+        // ---- epilogue: O / l -> bf16 -> global --------------------------------
+        ptx::mbar_wait(b_pv_done, (uint32_t)(n_blocks - 1) & 1u, 12);
+        ptx::tc_fence_after();
+        const float inv_l = 1.0f / l_sum;
+        const int q_row = m_blk * BM + row;
+        __nv_bfloat16* orow = prm.o + (int64_t)b * prm.o_sb + (int64_t)q_row * prm.o_sn +
+                              (int64_t)h * prm.o_sh;
+#pragma unroll
+        for (int c = 0; c < HD / 32; ++c) {
+            uint32_t r[32];
+            ptx::tmem_ld32(tO + c * 32, r);
+            ptx::tmem_wait_ld();
+            if (q_row < prm.Nq) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[i + e]) * inv_l;
+                    *reinterpret_cast<Vec16*>(orow + c * 32 + i) = pack8<__nv_bfloat16>(f);
+                }
+            }
+        }
+        ptx::tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == 5) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------ host ---
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// [B, N, H, 64] bf16 with element strides (sb, sn, sh); box = 128 tokens x 64 of one head.
+static int make_map(CUtensorMap* m, const void* base, int B, int H, int N, int64_t sb, int64_t sn,
+                    int64_t sh, const char* what) {
+    EncodeTiledFn fn = get_encode_fn();
+    MVOC_REQUIRE(fn != nullptr, MVOC_ERR_DRIVER, "mvoc_attn_fwd: cuTensorMapEncodeTiled unavailable");
+    cuuint64_t dims[4] = {(cuuint64_t)HD, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)sh * 2, (cuuint64_t)sn * 2, (cuuint64_t)sb * 2};
+    // a size-1 dimension may carry any stride; TMA still wants a multiple of 16 bytes
+    if (H == 1) strides[0] = 128;
+    if (B == 1) strides[2] = (cuuint64_t)sn * 2 * (cuuint64_t)N;
+    cuuint32_t box[4] = {(cuuint32_t)HD, 1, (cuuint32_t)BM, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MVOC_REQUIRE(r == CUDA_SUCCESS, MVOC_ERR_DRIVER,
+                 "mvoc_attn_fwd: cuTensorMapEncodeTiled(%s) failed with CUresult %d "
+                 "(B=%d H=%d N=%d strides=%lld,%lld,%lld)",
+                 what, (int)r, B, H, N, (long long)sb, (long long)sn, (long long)sh);
+    return MVOC_OK;
+}
+
+template <bool kPInTmem, int kStages>
+static int launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                  const Params& prm, int B, int H, cudaStream_t s) {
+    using L = Smem<kPInTmem, kStages>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<kPInTmem, kStages>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, L::alloc);
+        MVOC_REQUIRE(e == cudaSuccess, MVOC_ERR_CUDA, "mvoc_attn_fwd: cudaFuncSetAttribute: %s",
+                     cudaGetErrorString(e));
+        attr_set = true;
+    }
+    dim3 grid((prm.Nq + BM - 1) / BM, H, B);
+    attn_fwd_kernel<kPInTmem, kStages><<<grid, THREADS, L::alloc, s>>>(mq, mk, mv, prm);
+    return check_launch("mvoc_attn_fwd");
+}
+
+}  // namespace attn
+}  // namespace mvoc
+
+using namespace mvoc;
+
+extern "C" int mvoc_attn_fwd(const void* q, const void* k, const void* v, void* o, int B, int H,
+                             int Nq, int Nk, int D, int64_t q_sb, int64_t q_sn, int64_t q_sh,
+                             int64_t k_sb, int64_t k_sn, int64_t k_sh, int64_t v_sb, int64_t v_sn,
+                             int64_t v_sh, int64_t o_sb, int64_t o_sn, int64_t o_sh, float scale,
+                             int dtype, int variant, void* stream) {
+    MVOC_REQUIRE(q && k && v && o, MVOC_ERR_INVALID_ARG, "mvoc_attn_fwd: null pointer");
+    MVOC_REQUIRE(dtype == MVOC_BF16, MVOC_ERR_UNSUPPORTED,
+                 "mvoc_attn_fwd: dtype %d unsupported (bf16 only)", dtype);
+    MVOC_REQUIRE(D == attn::HD, MVOC_ERR_UNSUPPORTED,
+                 "mvoc_attn_fwd: head_dim %d unsupported (64 only)", D);
+    MVOC_REQUIRE(B > 0 && H > 0 && Nq > 0 && Nk > 0, MVOC_ERR_INVALID_ARG,
+                 "mvoc_attn_fwd: empty problem B=%d H=%d Nq=%d Nk=%d", B, H, Nq, Nk);
+    MVOC_REQUIRE(B <= 65535 && H <= 65535, MVOC_ERR_UNSUPPORTED,
+                 "mvoc_attn_fwd: B=%d / H=%d exceed the grid limits", B, H);
+    MVOC_REQUIRE(variant >= 0 && variant <= 2, MVOC_ERR_INVALID_ARG,
+                 "mvoc_attn_fwd: unknown variant %d", variant);
+    const int64_t strides[12] = {q_sb, q_sn, q_sh, k_sb, k_sn, k_sh, v_sb, v_sn, v_sh, o_sb, o_sn, o_sh};
+    for (int i = 0; i < 12; ++i)
+        MVOC_REQUIRE(strides[i] % 8 == 0 && strides[i] >= 0, MVOC_ERR_UNSUPPORTED,
+                     "mvoc_attn_fwd: stride #%d = %lld is not a non-negative multiple of 8 elements",
+                     i, (long long)strides[i]);
+    MVOC_REQUIRE(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) &&
+                     ((uintptr_t)o % 16 == 0),
+                 MVOC_ERR_INVALID_ARG, "mvoc_attn_fwd: pointers must be 16-byte aligned");
+    CUtensorMap mq, mk, mv;
+    int rc;
+    if ((rc = attn::make_map(&mq, q, B, H, Nq, q_sb, q_sn, q_sh, "q")) != MVOC_OK) return rc;
+    if ((rc = attn::make_map(&mk, k, B, H, Nk, k_sb, k_sn, k_sh, "k")) != MVOC_OK) return rc;
+    if ((rc = attn::make_map(&mv, v, B, H, Nk, v_sb, v_sn, v_sh, "v")) != MVOC_OK) return rc;
+    attn::Params prm;
+    prm.o = (__nv_bfloat16*)o;
+    prm.o_sb = o_sb;
+    prm.o_sn = o_sn;
+    prm.o_sh = o_sh;
+    prm.Nq = Nq;
+    prm.Nk = Nk;
+    prm.scale_log2 = scale * 1.4426950408889634f;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (variant == 1) return attn::launch<false, 2>(mq, mk, mv, prm, B, H, s);
+    return attn::launch<true, 3>(mq, mk, mv, prm, B, H, s);
+}

@@ -1,0 +1,256 @@
+// Short-sequence ("temporal") attention: tokens = frames (T <= 32), D = 64.
+// Reference: F.scaled_dot_product_attention at i2vgen-xl/pnp_utils.py:862-864
+// and the stock processor behind attention_forward (:348-385) for the
+// temporal attn2 / transformer_in, all driven by
+// transformer_temporal_model_forward (:170-220) on [(b h w), T, C] tensors.
+//
+// Arithmetic intensity is ~8 FLOP/B (read Q,K,V + write O once), so this is an
+// HBM-bound kernel: one warp owns one (pixel, head) problem, pulls the three
+// T x 64 bf16 tiles with 16-byte cp.async (full 128-byte lines), runs the two
+// tiny GEMMs on mma.sync fragments (enough to stay under the memory time; a
+// tcgen05 tile would be 87 % padding at T = 16), and writes O back through
+// shared memory as full 128-byte rows.
+#include "common.cuh"
+
+namespace mvoc {
+
+constexpr int TA_WARPS = 4;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                        uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
+                                          uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2,
+                                               uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+// byte offset of 16-byte chunk `c` of row `r` in a 128-byte-row, XOR-swizzled tile
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+struct TAParams {
+    const __nv_bfloat16 *q, *k, *v;
+    __nv_bfloat16* o;
+    int64_t P;
+    int H;
+    int64_t q_sp, q_st, q_sh, k_sp, k_st, k_sh, v_sp, v_st, v_sh, o_sp, o_st, o_sh;
+    float scale_log2;
+};
+
+template <int T>
+__global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal_kernel(TAParams p) {
+    constexpr int MT = (T + 15) / 16;   // query m-tiles
+    constexpr int TP = MT * 16;         // padded rows held in smem
+    constexpr int NT = T / 8;           // key n-tiles (exact)
+    constexpr int KT = MT;              // PV k-steps of 16 keys
+    constexpr int TILE = TP * 128;      // bytes per matrix
+    extern __shared__ __align__(128) uint8_t ta_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)blockIdx.x * TA_WARPS + warp;
+    if (item >= p.P * p.H) return;
+    const int64_t prob = item / p.H;
+    const int h = (int)(item % p.H);
+    const uint32_t sQ = smem_u32(ta_smem) + warp * 3 * TILE, sK = sQ + TILE, sV = sK + TILE;
+
+    const __nv_bfloat16* gq = p.q + prob * p.q_sp + (int64_t)h * p.q_sh;
+    const __nv_bfloat16* gk = p.k + prob * p.k_sp + (int64_t)h * p.k_sh;
+    const __nv_bfloat16* gv = p.v + prob * p.v_sp + (int64_t)h * p.v_sh;
+#pragma unroll
+    for (int i = 0; i < (T * 8) / 32; ++i) {
+        const int idx = lane + 32 * i, r = idx >> 3, c = idx & 7;
+        cp_async16(sQ + swz(r, c), gq + (int64_t)r * p.q_st + c * 8);
+        cp_async16(sK + swz(r, c), gk + (int64_t)r * p.k_st + c * 8);
+        cp_async16(sV + swz(r, c), gv + (int64_t)r * p.v_st + c * 8);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (TP > T) {  // zero the padding rows (T = 8 or 24)
+        const Vec16 z = {{0u, 0u, 0u, 0u}};
+        for (int idx = lane; idx < (TP - T) * 8; idx += 32) {
+            const int r = T + (idx >> 3), c = idx & 7;
+            uint8_t* base = ta_smem + warp * 3 * TILE;
+            *reinterpret_cast<Vec16*>(base + swz(r, c)) = z;
+            *reinterpret_cast<Vec16*>(base + TILE + swz(r, c)) = z;
+            *reinterpret_cast<Vec16*>(base + 2 * TILE + swz(r, c)) = z;
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+
+    const int g = lane >> 2, t = lane & 3;
+    const int mat = lane >> 3, mr = lane & 7;
+    __nv_bfloat16* go = p.o + prob * p.o_sp + (int64_t)h * p.o_sh;
+
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        // ---- S = Q K^T for this m-tile -----------------------------------
+        float s[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+#pragma unroll
+        for (int ks = 0; ks < 4; ks += 2) {
+            uint32_t a[2][4];
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const int row = mt * 16 + (mat & 1) * 8 + mr;
+                const int chunk = 2 * (ks + kk) + (mat >> 1);
+                ldsm_x4(sQ + swz(row, chunk), a[kk][0], a[kk][1], a[kk][2], a[kk][3]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(sK + swz(nt * 8 + mr, 2 * ks + mat), b0, b1, b2, b3);
+                mma_bf16_16816(s[nt], a[0][0], a[0][1], a[0][2], a[0][3], b0, b1);
+                mma_bf16_16816(s[nt], a[1][0], a[1][1], a[1][2], a[1][3], b2, b3);
+            }
+        }
+        // ---- softmax over keys (rows g and g+8 of the tile) ---------------
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+            m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        const float o0 = -m0 * p.scale_log2, o1 = -m1 * p.scale_log2;
+        float l0 = 0.0f, l1 = 0.0f;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            s[nt][0] = exp2f(fmaf(s[nt][0], p.scale_log2, o0));
+            s[nt][1] = exp2f(fmaf(s[nt][1], p.scale_log2, o0));
+            s[nt][2] = exp2f(fmaf(s[nt][2], p.scale_log2, o1));
+            s[nt][3] = exp2f(fmaf(s[nt][3], p.scale_log2, o1));
+            l0 += s[nt][0] + s[nt][1];
+            l1 += s[nt][2] + s[nt][3];
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        // ---- O = P V ------------------------------------------------------
+        float o[8][4];
+#pragma unroll
+        for (int dn = 0; dn < 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.0f;
+#pragma unroll
+        for (int kk = 0; kk < KT; ++kk) {
+            const bool hi_valid = (2 * kk + 1) < NT;  // compile-time after unrolling
+            const uint32_t a0 = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
+            const uint32_t a1 = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
+            const uint32_t a2 = hi_valid ? pack_bf16x2(s[hi_valid ? 2 * kk + 1 : 0][0], s[hi_valid ? 2 * kk + 1 : 0][1]) : 0u;
+            const uint32_t a3 = hi_valid ? pack_bf16x2(s[hi_valid ? 2 * kk + 1 : 0][2], s[hi_valid ? 2 * kk + 1 : 0][3]) : 0u;
+#pragma unroll
+            for (int dn = 0; dn < 8; dn += 2) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4_t(sV + swz(16 * kk + (mat & 1) * 8 + mr, dn + (mat >> 1)), b0, b1, b2, b3);
+                mma_bf16_16816(o[dn], a0, a1, a2, a3, b0, b1);
+                mma_bf16_16816(o[dn + 1], a0, a1, a2, a3, b2, b3);
+            }
+        }
+        // ---- normalise, stage in the Q rows of this m-tile, write out ------
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        uint8_t* stage = ta_smem + warp * 3 * TILE;
+        __syncwarp();
+#pragma unroll
+        for (int dn = 0; dn < 8; ++dn) {
+            *reinterpret_cast<uint32_t*>(stage + swz(mt * 16 + g, dn) + t * 4) =
+                pack_bf16x2(o[dn][0] * i0, o[dn][1] * i0);
+            *reinterpret_cast<uint32_t*>(stage + swz(mt * 16 + g + 8, dn) + t * 4) =
+                pack_bf16x2(o[dn][2] * i1, o[dn][3] * i1);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = lane + 32 * i, r = mt * 16 + (idx >> 3), c = idx & 7;
+            if (r < T) {
+                const Vec16 v = *reinterpret_cast<const Vec16*>(stage + swz(r, c));
+                st_stream16(go + (int64_t)r * p.o_st + c * 8, v);
+            }
+        }
+    }
+}
+
+template <int T>
+static int ta_launch(const TAParams& p, cudaStream_t s) {
+    constexpr int TP = ((T + 15) / 16) * 16;
+    const size_t smem = (size_t)TA_WARPS * 3 * TP * 128;
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        cudaFuncSetAttribute(attn_temporal_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
+        attr_set = true;
+    }
+    const int64_t items = p.P * p.H;
+    const int64_t grid = (items + TA_WARPS - 1) / TA_WARPS;
+    attn_temporal_kernel<T><<<(unsigned)grid, TA_WARPS * 32, smem, s>>>(p);
+    return check_launch("mvoc_attn_temporal_fwd");
+}
+
+}  // namespace mvoc
+
+using namespace mvoc;
+
+extern "C" int mvoc_attn_temporal_fwd(const void* q, const void* k, const void* v, void* o,
+                                      int64_t P, int T, int H, int D, int64_t q_sp, int64_t q_st,
+                                      int64_t q_sh, int64_t k_sp, int64_t k_st, int64_t k_sh,
+                                      int64_t v_sp, int64_t v_st, int64_t v_sh, int64_t o_sp,
+                                      int64_t o_st, int64_t o_sh, float scale, int dtype,
+                                      void* stream) {
+    MVOC_REQUIRE(q && k && v && o, MVOC_ERR_INVALID_ARG, "mvoc_attn_temporal_fwd: null pointer");
+    MVOC_REQUIRE(dtype == MVOC_BF16, MVOC_ERR_UNSUPPORTED,
+                 "mvoc_attn_temporal_fwd: dtype %d unsupported (bf16 only)", dtype);
+    MVOC_REQUIRE(D == 64, MVOC_ERR_UNSUPPORTED, "mvoc_attn_temporal_fwd: head_dim %d unsupported (64 only)", D);
+    MVOC_REQUIRE(P >= 0 && H > 0, MVOC_ERR_INVALID_ARG, "mvoc_attn_temporal_fwd: bad P/H");
+    MVOC_REQUIRE(P * H < ((int64_t)1 << 31) * TA_WARPS, MVOC_ERR_UNSUPPORTED,
+                 "mvoc_attn_temporal_fwd: too many problems");
+    const int64_t strides[12] = {q_sp, q_st, q_sh, k_sp, k_st, k_sh, v_sp, v_st, v_sh, o_sp, o_st, o_sh};
+    for (int i = 0; i < 12; ++i)
+        MVOC_REQUIRE(strides[i] % 8 == 0, MVOC_ERR_UNSUPPORTED,
+                     "mvoc_attn_temporal_fwd: stride #%d = %lld is not a multiple of 8 elements", i,
+                     (long long)strides[i]);
+    MVOC_REQUIRE(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) &&
+                     ((uintptr_t)o % 16 == 0),
+                 MVOC_ERR_INVALID_ARG, "mvoc_attn_temporal_fwd: pointers must be 16-byte aligned");
+    if (P == 0) return MVOC_OK;
+    TAParams p;
+    p.q = (const __nv_bfloat16*)q;
+    p.k = (const __nv_bfloat16*)k;
+    p.v = (const __nv_bfloat16*)v;
+    p.o = (__nv_bfloat16*)o;
+    p.P = P;
+    p.H = H;
+    p.q_sp = q_sp; p.q_st = q_st; p.q_sh = q_sh;
+    p.k_sp = k_sp; p.k_st = k_st; p.k_sh = k_sh;
+    p.v_sp = v_sp; p.v_st = v_st; p.v_sh = v_sh;
+    p.o_sp = o_sp; p.o_st = o_st; p.o_sh = o_sh;
+    p.scale_log2 = scale * 1.4426950408889634f;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (T) {
+        case 8: return ta_launch<8>(p, s);
+        case 16: return ta_launch<16>(p, s);
+        case 24: return ta_launch<24>(p, s);
+        case 32: return ta_launch<32>(p, s);
+        default:
+            set_error("mvoc_attn_temporal_fwd: T=%d unsupported (8, 16, 24 or 32 frames)", T);
+            return MVOC_ERR_UNSUPPORTED;
+    }
+}

@@ -1,0 +1,266 @@
+"""Tensor-facing wrappers over the C-ABI (include/mvoc_b200.h).
+
+PyTorch is used here only as the owner of device memory and streams: every
+function marshals ``data_ptr()``, shapes, strides and the current CUDA stream
+into one C call.  None of them has a torch/CPU fallback — a non-CUDA tensor or a
+missing library raises.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import _cabi
+from ._cabi import MVOC_MASK_F32, MVOC_MASK_U8
+
+_DT = {torch.bfloat16: _cabi.MVOC_BF16, torch.float16: _cabi.MVOC_F16, torch.float32: _cabi.MVOC_F32}
+HEAD_DIM = 64
+
+# number of C-ABI kernel launches issued through this module (bench.py's gpu_launches)
+launch_count = 0
+
+
+def _count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"mvoc_b200: unsupported dtype {t.dtype}") from None
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "mvoc_b200 ops run on CUDA tensors only (sm_100a kernels; there is no CPU fallback)"
+            )
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _bnc_strides(t: torch.Tensor, heads: int):
+    """(batch, token, head) element strides of a [B, N, heads*64] tensor."""
+    if t.dim() != 3 or t.shape[-1] != heads * HEAD_DIM or t.stride(-1) != 1:
+        raise ValueError(
+            f"expected [B, N, {heads}*{HEAD_DIM}] with a contiguous last dim, got {tuple(t.shape)} "
+            f"strides {t.stride()}"
+        )
+    return t.stride(0), t.stride(1), HEAD_DIM
+
+
+def attention(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    heads: int,
+    scale: Optional[float] = None,
+    out: Optional[torch.Tensor] = None,
+    variant: int = 0,
+) -> torch.Tensor:
+    """softmax(Q K^T * scale) V for q [B,Nq,H*64], k/v [B,Nk,H*64] -> [B,Nq,H*64] (tcgen05 kernel)."""
+    _need_cuda(q, k, v, out)
+    B, Nq, C = q.shape
+    Nk = k.shape[1]
+    if k.shape[0] != B or v.shape != k.shape:
+        raise ValueError(f"attention: q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)} mismatch")
+    if out is None:
+        out = torch.empty((B, Nq, C), dtype=q.dtype, device=q.device)
+    if scale is None:
+        scale = HEAD_DIM ** -0.5
+    lib = _cabi.load()
+    st = lib.mvoc_attn_fwd(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+        B, heads, Nq, Nk, HEAD_DIM,
+        *_bnc_strides(q, heads), *_bnc_strides(k, heads), *_bnc_strides(v, heads),
+        *_bnc_strides(out, heads),
+        float(scale), _dt(q), int(variant), _stream(),
+    )
+    _cabi.check(st, "mvoc_attn_fwd")
+    _count()
+    return out
+
+
+def temporal_attention(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    heads: int,
+    scale: Optional[float] = None,
+    out: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """Attention over frames: q,k,v [P, T, H*64] with T in {8,16,24,32} (warp-per-problem kernel)."""
+    _need_cuda(q, k, v, out)
+    P, T, C = q.shape
+    if k.shape != q.shape or v.shape != q.shape:
+        raise ValueError("temporal_attention: q, k, v must have the same shape")
+    if out is None:
+        out = torch.empty((P, T, C), dtype=q.dtype, device=q.device)
+    if scale is None:
+        scale = HEAD_DIM ** -0.5
+    lib = _cabi.load()
+    st = lib.mvoc_attn_temporal_fwd(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+        P, T, heads, HEAD_DIM,
+        *_bnc_strides(q, heads), *_bnc_strides(k, heads), *_bnc_strides(v, heads),
+        *_bnc_strides(out, heads),
+        float(scale), _dt(q), _stream(),
+    )
+    _cabi.check(st, "mvoc_attn_temporal_fwd")
+    _count()
+    return out
+
+
+def qk_blend_(
+    q: torch.Tensor,
+    k: Optional[torch.Tensor],
+    mask: torch.Tensor,
+    n_obj: int,
+    inject_background: bool,
+) -> None:
+    """In-place Q/K injection.  q,k: contiguous [n_branches*c, ...] whose slot-major flattening is
+    [n_branches, tokens, C]; mask [n_obj, tokens] uint8 (select) or float32 (lerp), same token order."""
+    _need_cuda(q, k, mask)
+    nb = n_obj + 3
+    C = q.shape[-1]
+    if not q.is_contiguous() or (k is not None and not k.is_contiguous()):
+        raise ValueError("qk_blend_: q and k must be contiguous")
+    if q.numel() % (nb * C) != 0:
+        raise ValueError(f"qk_blend_: {tuple(q.shape)} is not divisible into {nb} slots")
+    tokens = q.numel() // (nb * C)
+    if mask.dtype == torch.uint8:
+        kind = MVOC_MASK_U8
+    elif mask.dtype == torch.float32:
+        kind = MVOC_MASK_F32
+    else:
+        raise TypeError(f"qk_blend_: mask dtype {mask.dtype} (need uint8 or float32)")
+    if tuple(mask.shape) != (n_obj, tokens) or not mask.is_contiguous():
+        raise ValueError(f"qk_blend_: mask must be contiguous [{n_obj}, {tokens}], got {tuple(mask.shape)}")
+    base = 0 if inject_background else n_obj + 2
+    lib = _cabi.load()
+    st = lib.mvoc_qk_blend(q.data_ptr(), _ptr(k), n_obj, tokens, C, mask.data_ptr(), kind, base,
+                           _dt(q), _stream())
+    _cabi.check(st, "mvoc_qk_blend")
+    _count()
+
+
+def feature_blend_(x: torch.Tensor, mask: torch.Tensor, n_obj: int, frames: int) -> None:
+    """In-place hidden-state injection on x [n_branches*T, C, H, W]; mask [n_obj, T, H*W] uint8."""
+    _need_cuda(x, mask)
+    nb = n_obj + 3
+    if x.dim() != 4 or not x.is_contiguous() or x.shape[0] != nb * frames:
+        raise ValueError(f"feature_blend_: need contiguous [{nb}*{frames}, C, H, W], got {tuple(x.shape)}")
+    C, HW = x.shape[1], x.shape[2] * x.shape[3]
+    if mask.dtype != torch.uint8 or tuple(mask.shape) != (n_obj, frames, HW) or not mask.is_contiguous():
+        raise ValueError(f"feature_blend_: mask must be contiguous uint8 [{n_obj}, {frames}, {HW}]")
+    lib = _cabi.load()
+    st = lib.mvoc_feature_blend(x.data_ptr(), n_obj, frames, C, HW, mask.data_ptr(), _dt(x), _stream())
+    _cabi.check(st, "mvoc_feature_blend")
+    _count()
+
+
+_gn_ws: dict = {}
+
+
+def groupnorm_silu(
+    x: torch.Tensor,
+    weight: torch.Tensor,
+    bias: torch.Tensor,
+    groups: int,
+    eps: float,
+    silu: bool,
+    frames_per_stat: int = 1,
+    out: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """GroupNorm(+SiLU) over x [N, C, *spatial]; statistics shared by `frames_per_stat` consecutive n."""
+    _need_cuda(x, weight, bias, out)
+    if not x.is_contiguous():
+        raise ValueError("groupnorm_silu: x must be contiguous")
+    N, C = x.shape[0], x.shape[1]
+    S = x.numel() // (N * C)
+    if out is None:
+        out = torch.empty_like(x)
+    lib = _cabi.load()
+    need = lib.mvoc_groupnorm_workspace_bytes(N, groups)
+    key = x.device.index
+    ws = _gn_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=x.device)
+        _gn_ws[key] = ws
+    if weight.dtype != x.dtype or bias.dtype != x.dtype:
+        raise TypeError("groupnorm_silu: weight/bias dtype must match x")
+    st = lib.mvoc_groupnorm_silu(x.data_ptr(), out.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                                 N, C, S, groups, frames_per_stat, float(eps), int(bool(silu)),
+                                 _dt(x), ws.data_ptr(), _stream())
+    _cabi.check(st, "mvoc_groupnorm_silu")
+    _count()
+    return out
+
+
+def latent_composite_(
+    z: torch.Tensor,
+    bg: torch.Tensor,
+    objs: torch.Tensor,
+    mask: Optional[torch.Tensor],
+    unet_in: Optional[torch.Tensor],
+    ratio: float,
+    do_fusion: bool,
+    obj_noise_fusion: bool = False,
+) -> None:
+    """Noise fusion of z [4,T,h,w]-shaped latents + concat into unet_in [n_obj+3, ...] (one launch)."""
+    _need_cuda(z, bg, objs, mask, unet_in)
+    E = z.numel()
+    n_obj = objs.numel() // E
+    for t in (z, bg, objs):
+        if not t.is_contiguous():
+            raise ValueError("latent_composite_: latents must be contiguous")
+    thw = E // 4
+    if mask is not None and (mask.dtype != torch.float32 or mask.numel() != n_obj * thw or not mask.is_contiguous()):
+        raise ValueError(f"latent_composite_: mask must be contiguous float32 [{n_obj}, {thw}]")
+    if unet_in is not None and (unet_in.numel() != (n_obj + 3) * E or not unet_in.is_contiguous()):
+        raise ValueError("latent_composite_: unet_in must be contiguous [n_obj+3, E]")
+    lib = _cabi.load()
+    st = lib.mvoc_latent_composite(z.data_ptr(), bg.data_ptr(), objs.data_ptr(), _ptr(mask),
+                                   _ptr(unet_in), n_obj, E, thw, float(ratio), int(bool(do_fusion)),
+                                   int(bool(obj_noise_fusion)), _dt(z),
+                                   _dt(unet_in) if unet_in is not None else _dt(z), _stream())
+    _cabi.check(st, "mvoc_latent_composite")
+    _count()
+
+
+def cfg_ddim_step_(pred_uncond: torch.Tensor, pred_cond: Optional[torch.Tensor], x: torch.Tensor,
+                   guidance: float, alpha_t: float, alpha_prev: float) -> None:
+    """x <- DDIM(v-pred, eta=0) step using v = u + g (c - u); in place on x."""
+    _need_cuda(pred_uncond, pred_cond, x)
+    if not (pred_uncond.is_contiguous() and x.is_contiguous() and (pred_cond is None or pred_cond.is_contiguous())):
+        raise ValueError("cfg_ddim_step_: tensors must be contiguous")
+    lib = _cabi.load()
+    st = lib.mvoc_cfg_ddim_step(pred_uncond.data_ptr(), _ptr(pred_cond), x.data_ptr(), x.numel(),
+                                float(guidance), float(alpha_t), float(alpha_prev),
+                                _dt(pred_uncond), _dt(x), _stream())
+    _cabi.check(st, "mvoc_cfg_ddim_step")
+    _count()
+
+
+def ddim_inverse_step_(pred_uncond: torch.Tensor, pred_cond: Optional[torch.Tensor], x: torch.Tensor,
+                       guidance: float, alpha_src: float, alpha_dst: float) -> None:
+    """x <- inverse-DDIM step from level alpha_src to alpha_dst; in place on x."""
+    _need_cuda(pred_uncond, pred_cond, x)
+    if not (pred_uncond.is_contiguous() and x.is_contiguous() and (pred_cond is None or pred_cond.is_contiguous())):
+        raise ValueError("ddim_inverse_step_: tensors must be contiguous")
+    lib = _cabi.load()
+    st = lib.mvoc_ddim_inverse_step(pred_uncond.data_ptr(), _ptr(pred_cond), x.data_ptr(), x.numel(),
+                                    float(guidance), float(alpha_src), float(alpha_dst),
+                                    _dt(pred_uncond), _dt(x), _stream())
+    _cabi.check(st, "mvoc_ddim_inverse_step")
+    _count()

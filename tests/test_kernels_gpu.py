@@ -1,0 +1,289 @@
+"""GPU parity tests: every C-ABI kernel against the fp32 oracle op on identical bf16-rounded inputs.
+
+Bars: binary-mask blends bit-exact; GN / soft blends / DDIM relative L2 <= 3e-3
+(one bf16 rounding); attention relative L2 <= 1e-2 (bf16 P in the P.V product).
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import ops_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
+    a = a.float().cpu()
+    b = b.float().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-20))
+
+
+def make_masks(n_obj, T, H, W, seed=0, device="cpu"):
+    """Moving soft-edged ellipses (float in [0,1], bool = float > 10/255) shaped [1,4,T,H,W]."""
+    g = torch.Generator().manual_seed(seed)
+    ys = torch.arange(H).view(1, H, 1).float()
+    xs = torch.arange(W).view(1, 1, W).float()
+    out = []
+    for j in range(n_obj):
+        cy = H * (0.3 + 0.4 * torch.rand(1, generator=g)) + torch.linspace(0, H * 0.1, T).view(T, 1, 1)
+        cx = W * (0.2 + 0.6 * j / max(1, n_obj)) + torch.linspace(0, W * 0.15, T).view(T, 1, 1)
+        ry, rx = H * 0.18, W * 0.14
+        d = torch.sqrt(((ys - cy) / ry) ** 2 + ((xs - cx) / rx) ** 2)
+        edge = 2.0 / min(ry, rx)
+        mf = ((1.0 + edge - d) / edge).clamp(0, 1)
+        mf = (mf * 255).round() / 255
+        mb = mf > (10.0 / 255.0)
+        mf5 = mf[None, None].expand(1, 4, T, H, W).contiguous().to(device)
+        mb5 = mb[None, None].expand(1, 4, T, H, W).contiguous().to(device)
+        out.append((mf5, mb5))
+    return out
+
+
+# ------------------------------------------------------------------ attention
+ATTN_CASES = [
+    # B, H, Nq, Nk
+    (2, 5, 256, 256),
+    (1, 1, 128, 128),
+    (2, 2, 64, 64),      # 8x8 latents (l3)
+    (3, 10, 1024, 1024),
+    (2, 5, 256, 145),    # cross attention: ragged Nk
+    (1, 3, 200, 77),     # ragged Nq and Nk
+    (1, 5, 4096, 4096),  # l0 spatial
+    (1, 2, 880, 880),    # 22x40 (config 5 l2): not a tile multiple
+]
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("B,H,Nq,Nk", ATTN_CASES)
+def test_attention_vs_oracle(cuda_device, B, H, Nq, Nk, variant):
+    from mvoc_b200 import ops
+
+    torch.manual_seed(B * 1000 + Nq + Nk)
+    C = H * 64
+    q = torch.randn(B, Nq, C).bfloat16()
+    k = torch.randn(B, Nk, C).bfloat16()
+    v = torch.randn(B, Nk, C).bfloat16()
+    ref = ops_ref.sdpa_ref(q.float(), k.float(), v.float(), H)
+    out = ops.attention(q.to(cuda_device), k.to(cuda_device), v.to(cuda_device), H, variant=variant)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    err = rel_l2(out, ref)
+    assert err <= 1e-2, f"rel L2 {err:.3e} (variant {variant})"
+
+
+def test_attention_large_logits_and_strided(cuda_device):
+    """Peaked softmax (exercises the lazy O rescale) on q/k/v that are slices of one fused buffer."""
+    from mvoc_b200 import ops
+
+    torch.manual_seed(7)
+    B, H, N = 2, 5, 1024
+    C = H * 64
+    qkv = (torch.randn(B, N, 3 * C) * 3.0).bfloat16()
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    # make later keys much larger so the running max keeps growing
+    ramp = torch.linspace(0.2, 4.0, N).view(1, N, 1)
+    k = (k.float() * ramp).bfloat16()
+    qkv_d = torch.cat([q, k, v], dim=-1).to(cuda_device)
+    qd, kd, vd = qkv_d[..., :C], qkv_d[..., C:2 * C], qkv_d[..., 2 * C:]
+    ref = ops_ref.sdpa_ref(q.float(), k.float(), v.float(), H)
+    for variant in (1, 2):
+        out = ops.attention(qd, kd, vd, H, variant=variant)
+        torch.cuda.synchronize()
+        err = rel_l2(out, ref)
+        assert err <= 1e-2, f"rel L2 {err:.3e} (variant {variant})"
+
+
+def test_attention_rejects_bad_shapes(cuda_device):
+    from mvoc_b200 import _cabi, ops
+
+    q = torch.randn(1, 128, 96, device=cuda_device).bfloat16()
+    with pytest.raises((ValueError, _cabi.MvocError)):
+        ops.attention(q, q, q, heads=2)  # head_dim 48
+    q32 = torch.randn(1, 128, 64, device=cuda_device)
+    with pytest.raises(_cabi.MvocError):
+        ops.attention(q32, q32, q32, heads=1)  # fp32 unsupported, no fallback
+
+
+@pytest.mark.parametrize("P,T,H", [(1024, 16, 5), (300, 16, 10), (257, 8, 2), (64, 32, 20), (50, 24, 1)])
+def test_temporal_attention_vs_oracle(cuda_device, P, T, H):
+    from mvoc_b200 import ops
+
+    torch.manual_seed(P + T)
+    C = H * 64
+    q = torch.randn(P, T, C).bfloat16()
+    k = torch.randn(P, T, C).bfloat16()
+    v = torch.randn(P, T, C).bfloat16()
+    ref = ops_ref.sdpa_ref(q.float(), k.float(), v.float(), H)
+    out = ops.temporal_attention(q.to(cuda_device), k.to(cuda_device), v.to(cuda_device), H)
+    torch.cuda.synchronize()
+    err = rel_l2(out, ref)
+    assert err <= 1e-2, f"rel L2 {err:.3e}"
+
+
+# ------------------------------------------------------------------ blends
+def _token_masks_spatial(masks, h, w):
+    """[n_obj, T*h*w] uint8 in (frame, pixel) order from the bool masks (nearest-resized)."""
+    rows = []
+    for _, mb in masks:
+        m = ops_ref.nearest_mask(mb[0, 0].float(), h, w)  # [T,h,w]
+        rows.append((m > 0.5).to(torch.uint8).reshape(-1))
+    return torch.stack(rows).contiguous()
+
+
+def _token_masks_temporal(masks, h, w):
+    """[n_obj, h*w*T] float32 in (pixel, frame) order from the float masks (nearest-resized)."""
+    rows = []
+    for mf, _ in masks:
+        m = ops_ref.nearest_mask(mf[0, 0].float(), h, w)  # [T,h,w]
+        rows.append(m.permute(1, 2, 0).reshape(-1).float())
+    return torch.stack(rows).contiguous()
+
+
+@pytest.mark.parametrize("n_obj", [1, 2, 3])
+@pytest.mark.parametrize("inject_background", [False, True])
+def test_spatial_qk_blend_bit_exact(cuda_device, n_obj, inject_background):
+    from mvoc_b200 import ops
+
+    T, H, W, h, w, C = 8, 32, 32, 16, 16, 128
+    nb = n_obj + 3
+    masks = make_masks(n_obj, T, H, W, seed=n_obj)
+    torch.manual_seed(3)
+    q = torch.randn(nb * T, h * w, C).bfloat16()
+    k = torch.randn(nb * T, h * w, C).bfloat16()
+    q_ref, k_ref = ops_ref.spatial_qk_inject_ref(q.float(), k.float(), masks, h, w, inject_background)
+    qd, kd = q.to(cuda_device), k.to(cuda_device)
+    ops.qk_blend_(qd, kd, _token_masks_spatial(masks, h, w).to(cuda_device), n_obj, inject_background)
+    torch.cuda.synchronize()
+    assert torch.equal(qd.float().cpu(), q_ref)
+    assert torch.equal(kd.float().cpu(), k_ref)
+
+
+@pytest.mark.parametrize("n_obj", [1, 2, 3])
+@pytest.mark.parametrize("inject_background", [False, True])
+def test_temporal_qk_blend(cuda_device, n_obj, inject_background):
+    from mvoc_b200 import ops
+
+    T, H, W, h, w, C = 8, 32, 32, 16, 16, 64
+    nb = n_obj + 3
+    masks = make_masks(n_obj, T, H, W, seed=10 + n_obj)
+    torch.manual_seed(4)
+    q = torch.randn(nb * h * w, T, C).bfloat16()
+    k = torch.randn(nb * h * w, T, C).bfloat16()
+    q_ref, k_ref = ops_ref.temporal_qk_inject_ref(q.float(), k.float(), masks, h, w, inject_background)
+    qd, kd = q.to(cuda_device), k.to(cuda_device)
+    ops.qk_blend_(qd, kd, _token_masks_temporal(masks, h, w).to(cuda_device), n_obj, inject_background)
+    torch.cuda.synchronize()
+    # fp32 lerp rounded once to bf16: equal to the rounded oracle up to 1 ulp ties
+    assert rel_l2(qd, q_ref) <= 3e-3
+    assert rel_l2(kd, k_ref) <= 3e-3
+    assert torch.equal(qd.float().cpu()[: (n_obj + 1) * h * w], q.float()[: (n_obj + 1) * h * w])  # sources untouched
+
+
+@pytest.mark.parametrize("n_obj", [1, 2, 3])
+def test_feature_blend_bit_exact(cuda_device, n_obj):
+    from mvoc_b200 import ops
+
+    T, H, W, C = 8, 32, 32, 64
+    nb = n_obj + 3
+    masks = make_masks(n_obj, T, H, W, seed=20 + n_obj)
+    torch.manual_seed(5)
+    x = torch.randn(nb * T, C, H, W).bfloat16()
+    ref = ops_ref.feature_inject_ref(x.float(), masks)
+    m8 = torch.stack([mb[0, 0].reshape(T, H * W).to(torch.uint8) for _, mb in masks]).contiguous()
+    xd = x.to(cuda_device)
+    ops.feature_blend_(xd, m8.to(cuda_device), n_obj, T)
+    torch.cuda.synchronize()
+    assert torch.equal(xd.float().cpu(), ref)
+
+
+# ------------------------------------------------------------------ GroupNorm
+GN_CASES = [
+    # N, C, H, W, frames_per_stat, silu, eps
+    (16, 320, 32, 32, 1, True, 1e-5),     # slab path
+    (16, 320, 32, 32, 1, False, 1e-6),    # transformer norm
+    (8, 960, 64, 64, 1, True, 1e-5),      # slab too large for smem -> split path
+    (16, 64, 16, 16, 8, True, 1e-5),      # temporal (5-D) statistics
+    (16, 320, 32, 32, 8, False, 1e-6),
+    (4, 1280, 8, 8, 1, True, 1e-5),
+    (4, 64, 11, 20, 1, True, 1e-5),       # S % 8 != 0 -> scalar path
+]
+
+
+@pytest.mark.parametrize("N,C,H,W,fps,silu,eps", GN_CASES)
+def test_groupnorm_silu_vs_oracle(cuda_device, N, C, H, W, fps, silu, eps):
+    from mvoc_b200 import ops
+
+    torch.manual_seed(C + H)
+    x = (torch.randn(N, C, H, W) * 2.0 + 0.7).bfloat16()
+    wgt = (1.0 + 0.2 * torch.randn(C)).bfloat16()
+    bias = (0.1 * torch.randn(C)).bfloat16()
+    ref = ops_ref.group_norm_ref(x.float(), wgt.float(), bias.float(), 32, eps, silu, fps)
+    out = ops.groupnorm_silu(x.to(cuda_device), wgt.to(cuda_device), bias.to(cuda_device), 32, eps, silu, fps)
+    torch.cuda.synchronize()
+    err = rel_l2(out, ref)
+    assert err <= 3e-3, f"rel L2 {err:.3e}"
+    # in place
+    xd = x.to(cuda_device)
+    ops.groupnorm_silu(xd, wgt.to(cuda_device), bias.to(cuda_device), 32, eps, silu, fps, out=xd)
+    torch.cuda.synchronize()
+    assert torch.equal(xd, out)
+
+
+# ------------------------------------------------------------------ latent kernels
+@pytest.mark.parametrize("n_obj", [1, 2, 3])
+@pytest.mark.parametrize("onf", [False, True])
+def test_latent_composite_vs_oracle(cuda_device, n_obj, onf):
+    from mvoc_b200 import ops
+
+    T, h, w = 8, 32, 32
+    masks = make_masks(n_obj, T, h, w, seed=30 + n_obj)
+    torch.manual_seed(6)
+    z = torch.randn(1, 4, T, h, w)
+    bg = torch.randn(1, 4, T, h, w)
+    objs = [torch.randn(1, 4, T, h, w) for _ in range(n_obj)]
+    ratio = 0.3
+    ref = ops_ref.latent_fusion_ref(z, bg, objs, [m for m, _ in masks], ratio, onf)
+    zd, bgd = z.to(cuda_device).clone(), bg.to(cuda_device)
+    objd = torch.cat(objs).to(cuda_device).contiguous()
+    md = torch.stack([m[0, 0].reshape(-1) for m, _ in masks]).float().contiguous().to(cuda_device)
+    unet_in = torch.empty(n_obj + 3, 4, T, h, w, dtype=torch.bfloat16, device=cuda_device)
+    ops.latent_composite_(zd, bgd, objd, md, unet_in, ratio, True, onf)
+    torch.cuda.synchronize()
+    assert rel_l2(zd, ref) <= 1e-6
+    expect_in = torch.cat([bg, *objs, ref, ref]).bfloat16()
+    assert torch.equal(unet_in.cpu(), expect_in)
+    # non-fusion step: z untouched, pure concat
+    z2 = z.to(cuda_device).clone()
+    ops.latent_composite_(z2, bgd, objd, None, unet_in, ratio, False)
+    torch.cuda.synchronize()
+    assert torch.equal(z2.cpu(), z)
+    assert torch.equal(unet_in.cpu(), torch.cat([bg, *objs, z, z]).bfloat16())
+
+
+def test_cfg_ddim_step_vs_oracle(cuda_device):
+    from mvoc_b200 import ops
+
+    torch.manual_seed(8)
+    E = 4 * 8 * 32 * 32
+    u = torch.randn(E).bfloat16()
+    c = torch.randn(E).bfloat16()
+    x = torch.randn(E)
+    a_t, a_prev, g = 0.00078403, 0.00349756, 9.0
+    ref = ops_ref.ddim_step_ref(ops_ref.cfg_ref(u.float(), c.float(), g), x, a_t, a_prev)
+    xd = x.to(cuda_device).clone()
+    ops.cfg_ddim_step_(u.to(cuda_device), c.to(cuda_device), xd, g, a_t, a_prev)
+    torch.cuda.synchronize()
+    assert rel_l2(xd, ref) <= 1e-5
+    # known answer: x=1, v=0.5, 981 -> 961 => 0.983932
+    one = torch.ones(8, device=cuda_device)
+    half = torch.full((8,), 0.5, device=cuda_device)
+    ops.cfg_ddim_step_(half, None, one, 1.0, a_t, a_prev)
+    torch.cuda.synchronize()
+    assert abs(float(one[0]) - 0.983932) < 2e-5
+    # inverse step shares the algebra
+    x3 = x.to(cuda_device).clone()
+    ops.ddim_inverse_step_(u.to(cuda_device), None, x3, 1.0, a_prev, a_t)
+    torch.cuda.synchronize()
+    ref3 = ops_ref.ddim_step_ref(u.float(), x, a_prev, a_t)
+    assert rel_l2(x3, ref3) <= 1e-5
