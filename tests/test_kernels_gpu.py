@@ -251,8 +251,10 @@ def test_latent_composite_vs_oracle(cuda_device, n_obj, onf):
     ops.latent_composite_(zd, bgd, objd, md, unet_in, ratio, True, onf)
     torch.cuda.synchronize()
     assert rel_l2(zd, ref) <= 1e-6
-    expect_in = torch.cat([bg, *objs, ref, ref]).bfloat16()
-    assert torch.equal(unet_in.cpu(), expect_in)
+    src_in = torch.cat([bg, *objs]).bfloat16()
+    assert torch.equal(unet_in[: n_obj + 1].cpu(), src_in)          # sources: exact casts
+    zb = zd.cpu().bfloat16()                                          # composite slots: the kernel's own z
+    assert torch.equal(unet_in[n_obj + 1].cpu(), zb[0]) and torch.equal(unet_in[n_obj + 2].cpu(), zb[0])
     # non-fusion step: z untouched, pure concat
     z2 = z.to(cuda_device).clone()
     ops.latent_composite_(z2, bgd, objd, None, unet_in, ratio, False)
