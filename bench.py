@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — MVOC composition hot path on B200: video frames/s of the 50-step DDIM composition.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl mvoc|reference] [--workload config2]
+
+One "step" = one DDIM composition step (latent fusion + concat, one UNet forward over
+[bg, obj_1..obj_n, uncond, cond], CFG + DDIM update) of BASELINE.json configs[1]:
+full i2vgen-xl-architecture UNet (random init), 16 frames x 64x64 latents (512x512 px), bg + 2 objects,
+boat_surf injection schedule.  The timed region starts at step 0 of the schedule (fusion step, conv
+injection on the first 10 % of the steps) and runs K steps; with K = 50 (default) it is the whole run.
+value = n_frames / (50 * mean step time).
+
+Prints ONE JSON line (see README / DESIGN.md §Measurement for every key).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "video frames/s, 50-step 16x512^2 bg+2obj composite"
+UNIT = "frames/s"
+
+
+# --------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "power_w_max": max(power) if power else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def measured_peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        d["_source"] = "measured"
+        return d
+    # fallback stated in /opt/skills/guides/B200_PROFILING.md
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------- CPU arm (oracle port)
+class CpuSampler:
+    """Times the fp32 oracle (the reference path restated, oracle/pipeline.py) on the host cores for ONE
+    composition step of a bounded sample of the workload: the full UNet and all n_obj+3 branches, but 2 of
+    the n_frames frames at a latent size chosen from a GEMM calibration so that a step fits `budget_s`.
+    step() -> (frames_per_s_equivalent, seconds)."""
+
+    def __init__(self, wl_name: str, budget_s: float):
+        import torch
+
+        from mvoc_b200 import synthetic
+        from oracle import pipeline as opipe
+        from oracle.scheduler import DDIMScheduler
+
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        full = synthetic.WORKLOADS[wl_name]
+        a = torch.randn(2048, 2048)
+        b = torch.randn(2048, 2048)
+        a @ b
+        t0 = time.perf_counter()
+        for _ in range(3):
+            a @ b
+        gemm_tfs = 3 * 2 * 2048 ** 3 / (time.perf_counter() - t0) / 1e12
+        # ~104 TFLOP per full step at 16 x 64x64 x 5 branches => per (frame, latent pixel)
+        flop_per_frame_pixel = 104.1e12 / (16 * 64 * 64)
+        eff = 0.5 * gemm_tfs * 1e12  # convs / attention run below the GEMM rate
+        frames, side = 2, 16
+        for s in (64, 32, 16):
+            if flop_per_frame_pixel * frames * s * s / eff <= budget_s:
+                side = s
+                break
+        self.full = full
+        self.wl = synthetic.Workload(
+            f"{wl_name}-cpu-sample", full.unet, frames, side, side, full.n_obj, n_steps=full.n_steps, cfg=full.cfg,
+            pnp_f_t=full.pnp_f_t, pnp_spatial_attn_t=full.pnp_spatial_attn_t, pnp_temp_attn_t=full.pnp_temp_attn_t,
+            fusion_step=full.fusion_step, random_noise_ratio=full.random_noise_ratio)
+        sched = DDIMScheduler()
+        sched.set_timesteps(self.wl.n_steps)
+        self.inputs = synthetic.make_inputs(self.wl, [int(t) for t in sched.timesteps], sched.alphas_cumprod)
+        self.unet = opipe.build_unet(self.wl.unet, seed=0)
+        self._loop = opipe.composite_loop
+        # frames of the 64x64 x 16-frame job per sample step if the per-(frame, latent pixel) cost stayed what it
+        # is in the sample (optimistic for the CPU: spatial attention grows quadratically with the latent area)
+        self.frame_equiv = frames * (side * side) / float(full.latent_h * full.latent_w)
+        self.desc = (f"oracle fp32 (oracle/pipeline.py), 1 composition step, full UNet, {self.wl.n_branches} "
+                     f"branches, {frames} of {full.n_frames} frames at {side}x{side} of "
+                     f"{full.latent_h}x{full.latent_w} latents; scaled per (frame x latent pixel) and "
+                     f"x{full.n_steps} steps (extrapolated, not a full run); host fp32 GEMM {gemm_tfs:.2f} TF/s")
+
+    def step(self):
+        t0 = time.perf_counter()
+        self._loop(self.unet, self.wl, self.inputs, max_steps=1)
+        dt = time.perf_counter() - t0
+        return self.frame_equiv / (self.full.n_steps * dt), dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port: diffusers and the
+    checkpoint are unavailable offline) on all host threads; rank 0 only."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    n = args.steps + args.warmup
+    budget = max(1.0, min(20.0, 150.0 / max(1, n)))
+    sampler = CpuSampler(args.workload, budget)
+    vals, t_start = [], time.perf_counter()
+    for i in range(n):
+        fps, dt = sampler.step()
+        if i >= args.warmup:
+            vals.append((fps, dt))
+        if time.perf_counter() - t_start > 240 and vals:  # hard bound on the whole arm
+            break
+    last = (sampler.cores, sampler.desc)
+    fps = statistics.mean(v for v, _ in vals)
+    ms = statistics.mean(d for _, d in vals) * 1e3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload + " (bounded CPU sample per step)"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": last[0], "kind": "port", "sample": last[1]},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_mvoc(args):
+    import torch
+
+    rank, world, local = dist_env()
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (sm_100a); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    from mvoc_b200 import _cabi, ops, synthetic
+    from mvoc_b200.parallel import FrameParallel
+    from mvoc_b200.pipeline import Conditioning, I2VGenXLPipeline, LatentBank, init_pnp
+    from mvoc_b200.scheduler import DDIMSchedule
+    from mvoc_b200.unet3d import build_unet
+
+    lib = _cabi.load()
+    _cabi.check(lib.mvoc_device_check(local), "mvoc_device_check")
+    par = FrameParallel.from_env(dev)  # world_size 1 => no-op
+
+    wl = synthetic.WORKLOADS[args.workload]
+    sched = DDIMSchedule(wl.n_steps)
+    inputs = synthetic.make_inputs(wl, sched.timesteps, sched.alphas_cumprod)
+    torch.backends.cudnn.benchmark = True
+    unet = build_unet(wl.unet, seed=0, device=dev)
+    pipe = I2VGenXLPipeline(unet, dev, parallel=par)
+    init_pnp(pipe, sched, wl)
+    bf = lambda x: x.to(device=dev, dtype=torch.bfloat16)
+    cond = Conditioning(bf(inputs["prompt_embeds"]), bf(inputs["image_embeddings"]),
+                        bf(inputs["image_latents_first"]), bf(inputs["image_latents"]), inputs["fps"].to(dev))
+    banks = [LatentBank(src, dev, pin_host=True) for src in inputs["source_latents"]]
+    masks = [(mf.to(dev), mb.to(dev)) for mf, mb in inputs["masks"]]
+
+    def loop(start, steps, host_io=False, lat=None):
+        lat = inputs["init_latents"].to(dev).clone() if lat is None else lat
+        return pipe.sample_with_pnp_pipeline_with_edit_prompt_extraction_with_attn_injection(
+            cond, lat, banks[0], banks[1:], masks, num_inference_steps=wl.n_steps, guidance_scale=wl.cfg,
+            ddim_init_latents_t_idx=wl.ddim_init_latents_t_idx, fusion_steps=tuple(wl.fusion_step),
+            random_noise_ratio=wl.random_noise_ratio, obj_random_noise_fusion=wl.obj_random_noise_fusion,
+            start_step=start, max_steps=steps, host_io=host_io)
+
+    K, W = args.steps, max(args.warmup, 0)
+    K = min(K, wl.n_steps)
+    # warm-up: W steps from the start of the schedule (cuDNN autotune, caches), state discarded
+    if W > 0:
+        loop(0, min(W, wl.n_steps))
+    torch.cuda.synchronize()
+
+    def barrier():
+        par.barrier()
+        torch.cuda.synchronize()
+
+    # ---- timed region 1: inputs resident in HBM ------------------------------------------------
+    timer = ops.KernelTimer()
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    launches0 = ops.launch_count
+    ops.set_timer(timer)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    final = loop(0, K)
+    ev1.record()
+    barrier()
+    ops.set_timer(None)
+    clk = clocks.stop() if rank == 0 else None
+    launches = ops.launch_count - launches0
+    ms_total = par.max_over_ranks(ev0.elapsed_time(ev1))
+    ms_step = ms_total / K
+
+    # ---- timed region 2: end to end through the pipeline API with host buffers ------------------
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record()
+    final_e2e = loop(0, K, host_io=True)
+    e1.record()
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    e2e_ms_step = par.max_over_ranks(max(e0.elapsed_time(e1), wall_ms)) / K
+    E = inputs["init_latents"].numel()
+    h2d = (1 + wl.n_obj) * E * 4
+    d2h = E * 4
+    same = bool(torch.equal(final, final_e2e))
+
+    if rank != 0:
+        return
+    peaks = measured_peaks()
+    frames_per_s = wl.n_frames / (wl.n_steps * ms_step / 1e3)
+    e2e_fps = wl.n_frames / (wl.n_steps * e2e_ms_step / 1e3)
+
+    # ---- roofline of the dominant kernel: l0 spatial self-attention (tcgen05) --------------------
+    summ = timer.summary()
+    attn_keys = [k for k in summ if k[0] == "attn"]
+    attn_ms = sum(summ[k][1] for k in attn_keys)
+    attn_flops = sum(summ[k][2] for k in attn_keys)
+    tattn_keys = [k for k in summ if k[0] == "attn_temporal"]
+    dom = max(attn_keys, key=lambda k: summ[k][1]) if attn_keys else None
+    roof = None
+    if dom is not None:
+        n, ms, work = summ[dom]
+        achieved = work / (ms / 1e3) / 1e12
+        peak = peaks["bf16_tflops_sustained"]
+        roof = {
+            "bound": "tensor", "kernel": f"attn_fwd_kernel B={dom[1]} H={dom[2]} Nq={dom[3]} Nk={dom[4]} D=64",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": peaks["_source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
+            "launches": n, "avg_launch_ms": ms / n, "share_of_step": ms / ms_total,
+            "traffic": None,
+        }
+    gn_keys = [k for k in summ if k[0] == "groupnorm"]
+    extra = {
+        "attn_tflops_all": (attn_flops / (attn_ms / 1e3) / 1e12) if attn_ms else None,
+        "attn_share_of_step": attn_ms / ms_total if ms_total else None,
+        "temporal_attn_gbs": (sum(summ[k][2] for k in tattn_keys) / (sum(summ[k][1] for k in tattn_keys) / 1e3) / 1e9)
+        if tattn_keys else None,
+        "groupnorm_gbs": (sum(summ[k][2] for k in gn_keys) / (sum(summ[k][1] for k in gn_keys) / 1e3) / 1e9)
+        if gn_keys else None,
+        "groupnorm_share_of_step": sum(summ[k][1] for k in gn_keys) / ms_total if gn_keys else None,
+    }
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
+    cpu = None
+    if args.gpus == 1 and not args.no_cpu_baseline:
+        try:
+            sampler = CpuSampler(args.workload, budget_s=20.0)
+            fps, dt = sampler.step()
+            cpu = {"value": fps, "unit": UNIT, "cores": sampler.cores, "kind": "port", "sample": sampler.desc,
+                   "seconds": dt}
+        except Exception as ex:  # the GPU numbers must still be reported
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+
+    line = {
+        "metric": METRIC, "value": frames_per_s, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {
+            "workload": f"{wl.name}: full i2vgen-xl UNet random-init, {wl.n_frames} frames x "
+                        f"{wl.latent_h}x{wl.latent_w} latents, bg+{wl.n_obj} objects, {wl.n_steps}-step DDIM "
+                        f"composition, cfg {wl.cfg}, pnp_f_t {wl.pnp_f_t}, spatial/temporal attn injection "
+                        f"{wl.pnp_spatial_attn_t}/{wl.pnp_temp_attn_t}",
+            "parallelism": par.describe(),
+            "l2": "activations per step (>= 210 MB per l0 tensor) exceed the 126 MB L2; no explicit flush",
+            "timed_steps_start_at": 0,
+        },
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms_step, "matches_device_resident_run": same},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "kernels": extra,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mvoc", choices=["mvoc", "reference"])
+    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_mvoc(args)
+
+
+if __name__ == "__main__":
+    main()

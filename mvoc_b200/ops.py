@@ -26,6 +26,53 @@ def _count(n: int = 1) -> None:
     launch_count += n
 
 
+class KernelTimer:
+    """Per-launch device timing with CUDA events on the launching stream (bench.py's roofline leg).
+    records[key] = list of (start_event, end_event, work) where work is algorithmic FLOPs or bytes."""
+
+    def __init__(self):
+        self.records = {}
+
+    def add(self, key, ev0, ev1, work):
+        self.records.setdefault(key, []).append((ev0, ev1, work))
+
+    def summary(self):
+        """key -> (launches, total_ms, total_work); call after torch.cuda.synchronize()."""
+        out = {}
+        for key, recs in self.records.items():
+            ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+            out[key] = (len(recs), ms, sum(w for _, _, w in recs))
+        return out
+
+
+_timer: Optional[KernelTimer] = None
+
+
+def set_timer(t: Optional[KernelTimer]) -> None:
+    global _timer
+    _timer = t
+
+
+class _Timed:
+    __slots__ = ("key", "work", "ev0")
+
+    def __init__(self, key, work):
+        self.key, self.work, self.ev0 = key, work, None
+
+    def __enter__(self):
+        if _timer is not None:
+            self.ev0 = torch.cuda.Event(enable_timing=True)
+            self.ev0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev0 is not None and _timer is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            _timer.add(self.key, self.ev0, ev1, self.work)
+        return False
+
+
 def _dt(t: torch.Tensor) -> int:
     try:
         return _DT[t.dtype]
@@ -79,13 +126,14 @@ def attention(
     if scale is None:
         scale = HEAD_DIM ** -0.5
     lib = _cabi.load()
-    st = lib.mvoc_attn_fwd(
-        q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
-        B, heads, Nq, Nk, HEAD_DIM,
-        *_bnc_strides(q, heads), *_bnc_strides(k, heads), *_bnc_strides(v, heads),
-        *_bnc_strides(out, heads),
-        float(scale), _dt(q), int(variant), _stream(),
-    )
+    with _Timed(("attn", B, heads, Nq, Nk), 4.0 * B * heads * Nq * Nk * HEAD_DIM):
+        st = lib.mvoc_attn_fwd(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+            B, heads, Nq, Nk, HEAD_DIM,
+            *_bnc_strides(q, heads), *_bnc_strides(k, heads), *_bnc_strides(v, heads),
+            *_bnc_strides(out, heads),
+            float(scale), _dt(q), int(variant), _stream(),
+        )
     _cabi.check(st, "mvoc_attn_fwd")
     _count()
     return out
@@ -109,13 +157,14 @@ def temporal_attention(
     if scale is None:
         scale = HEAD_DIM ** -0.5
     lib = _cabi.load()
-    st = lib.mvoc_attn_temporal_fwd(
-        q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
-        P, T, heads, HEAD_DIM,
-        *_bnc_strides(q, heads), *_bnc_strides(k, heads), *_bnc_strides(v, heads),
-        *_bnc_strides(out, heads),
-        float(scale), _dt(q), _stream(),
-    )
+    with _Timed(("attn_temporal", P, heads, T), 4.0 * P * T * C * q.element_size()):
+        st = lib.mvoc_attn_temporal_fwd(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+            P, T, heads, HEAD_DIM,
+            *_bnc_strides(q, heads), *_bnc_strides(k, heads), *_bnc_strides(v, heads),
+            *_bnc_strides(out, heads),
+            float(scale), _dt(q), _stream(),
+        )
     _cabi.check(st, "mvoc_attn_temporal_fwd")
     _count()
     return out
@@ -199,9 +248,10 @@ def groupnorm_silu(
         _gn_ws[key] = ws
     if weight.dtype != x.dtype or bias.dtype != x.dtype:
         raise TypeError("groupnorm_silu: weight/bias dtype must match x")
-    st = lib.mvoc_groupnorm_silu(x.data_ptr(), out.data_ptr(), weight.data_ptr(), bias.data_ptr(),
-                                 N, C, S, groups, frames_per_stat, float(eps), int(bool(silu)),
-                                 _dt(x), ws.data_ptr(), _stream())
+    with _Timed(("groupnorm", N, C, S, frames_per_stat), 2.0 * x.numel() * x.element_size()):
+        st = lib.mvoc_groupnorm_silu(x.data_ptr(), out.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                                     N, C, S, groups, frames_per_stat, float(eps), int(bool(silu)),
+                                     _dt(x), ws.data_ptr(), _stream())
     _cabi.check(st, "mvoc_groupnorm_silu")
     _count()
     return out
