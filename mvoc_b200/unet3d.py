@@ -55,8 +55,16 @@ class UNetConfig:
                           up_block_types=("UpBlock3D", "CrossAttnUpBlock3D"), transformer_in_heads=2)
 
     @staticmethod
+    def tiny4():
+        """Full 4-level layout with narrow channels (the golden-vector model of tests/golden)."""
+        return UNetConfig(block_out_channels=(64, 128, 256, 256), transformer_in_heads=2)
+
+    @staticmethod
     def named(kind: str):
-        return UNetConfig.full() if kind == "full" else UNetConfig.reduced()
+        try:
+            return {"full": UNetConfig.full, "reduced": UNetConfig.reduced, "tiny4": UNetConfig.tiny4}[kind]()
+        except KeyError:
+            raise ValueError(f"unknown UNet config {kind!r}") from None
 
 
 # ------------------------------------------------------------------ small pieces

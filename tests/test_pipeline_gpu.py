@@ -160,3 +160,38 @@ def test_invert_reduced(cuda_device, tmp_path):
         disk = load_ddim_latents_at_t(t, str(tmp_path))
         assert disk.shape == (1, 4, wl.n_frames, wl.latent_h, wl.latent_w)
         assert torch.equal(disk, saved[t].cpu())
+
+
+@pytest.mark.parametrize("case_name", ["all_hooks_t981", "attn_only_t481", "inject_bg_t481", "no_hooks_t21"])
+def test_unet_forward_vs_reference_golden(cuda_device, case_name):
+    """Product (bf16 kernels) against the output of the REFERENCE'S OWN code on the 4-level golden model
+    (tests/golden/unet_extension_forward_tiny4.pt, produced by tests/golden/make_golden.py)."""
+    import os
+
+    from mvoc_b200 import pnp_utils
+    from mvoc_b200.pipeline import Conditioning, I2VGenXLPipeline, init_pnp
+    from mvoc_b200.scheduler import DDIMSchedule
+    from mvoc_b200.unet3d import I2VGenXLUNet, UNetConfig
+    from tests.golden import spec
+
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "unet_extension_forward_tiny4.pt"),
+                      map_location="cpu")
+    case = next(c for c in spec.CASES if c["name"] == case_name)
+    ou = spec.build_tiny4(seed=0)
+    pu = I2VGenXLUNet(UNetConfig.tiny4()).eval().requires_grad_(False)
+    pu.load_state_dict(ou.state_dict(), strict=True)
+    pu = pu.to(cuda_device, torch.bfloat16)
+    pipe = I2VGenXLPipeline(pu, cuda_device)
+    cfg = SimpleNamespace(n_steps=50, pnp_f_t=case["pnp_f_t"], pnp_spatial_attn_t=case["pnp_spatial_attn_t"],
+                          pnp_temp_attn_t=case["pnp_temp_attn_t"], inject_background=case["inject_background"])
+    init_pnp(pipe, DDIMSchedule(50), cfg)
+    inp = spec.make_inputs(case)
+    masks = [(mf.to(cuda_device), mb.to(cuda_device)) for mf, mb in inp["masks"]]
+    pnp_utils.register_time_all(pipe, case["t"], masks)
+    out = pipe._unet_forward(inp["sample"].to(cuda_device, torch.bfloat16), case["t"], _cond(inp, cuda_device))
+    torch.cuda.synchronize()
+    ref = gold[case_name]
+    err = rel_l2(out, ref)
+    comp = rel_l2(out[3:], ref[3:])
+    print(f"[golden {case_name}] rel L2 all {err:.4e}, composite branches {comp:.4e}")
+    assert err <= 3e-2 and comp <= 3e-2
