@@ -87,6 +87,17 @@ int mvoc_attn_temporal_fwd(const void* q, const void* k, const void* v, void* o,
                            float scale, int dtype, void* stream);
 
 /*
+ * Same kernel with a two-level problem index (problem = outer * P_inner + inner), so that temporal
+ * attention reads channels-last activations [B, T, HW, C] in place — problem (b, pixel) starts at
+ * b*s_outer + pixel*s_inner and its frames are s_token apart — and the [(b t), c, h, w] ->
+ * [(b h w), t, c] permutes of i2vgen-xl/pnp_utils.py:189 and :207-213 are never materialised.
+ * strides16: element strides (outer, inner, token, head) for q, k, v, o in that order.
+ */
+int mvoc_attn_temporal_strided_fwd(const void* q, const void* k, const void* v, void* o,
+                                   int64_t P_outer, int64_t P_inner, int T, int H, int D,
+                                   const int64_t* strides16, float scale, int dtype, void* stream);
+
+/*
  * Q/K mask-blend injection, in place.
  * Replaces i2vgen-xl/pnp_utils.py:628-672 (spatial, binary mask) and
  * :782-850 (temporal, float mask).
@@ -130,6 +141,33 @@ int64_t mvoc_groupnorm_workspace_bytes(int64_t N, int G);
 int mvoc_groupnorm_silu(const void* x, void* y, const void* gamma, const void* beta,
                         int64_t N, int C, int64_t S, int G, int frames_per_stat,
                         float eps, int silu, int dtype, void* workspace, void* stream);
+
+/*
+ * Channels-last GroupNorm (+SiLU, + fused per-(n, channel) add) on [N, S, C]: the same reference call
+ * sites as mvoc_groupnorm_silu, for the NHWC host path; `add` [N, C] (nullable) fuses the resnet's
+ * `hidden_states + temb` (i2vgen-xl/pnp_utils.py:941-953) into the normalisation.
+ * Three launches so that the statistics of pixel shards can be merged across GPUs in between:
+ *   stats    -> partial [N, G, chunks] float2 (mean, M2); chunks from mvoc_groupnorm_nhwc_geometry
+ *   finalize -> stat [N / frames_per_stat, G] float2 (mean, rstd); merges `sets` partial arrays laid out
+ *               [sets, N, G, chunks] with element counts counts[sets, chunks] (float)
+ *   apply    -> y = silu?((x + add - mean) * rstd * gamma + beta); y may alias x
+ */
+int64_t mvoc_groupnorm_nhwc_partial_count(int64_t N, int G);
+int mvoc_groupnorm_nhwc_geometry(int64_t S, int C, int dtype, int* chunks, int64_t* tokens_per_chunk);
+int mvoc_groupnorm_nhwc_stats(const void* x, const void* add, void* partial, int64_t N, int64_t S, int C,
+                              int G, int dtype, void* stream);
+int mvoc_groupnorm_nhwc_finalize(const void* partial, const void* counts, void* stat, int64_t N, int G,
+                                 int chunks, int frames_per_stat, int sets, float eps, void* stream);
+int mvoc_groupnorm_nhwc_apply(const void* x, void* y, const void* gamma, const void* beta, const void* add,
+                              const void* stat, int64_t N, int64_t S, int C, int G, int frames_per_stat,
+                              int silu, int dtype, void* stream);
+
+/*
+ * Fused GEGLU gate: y[m, j] = x[m, j] * gelu(x[m, F + j]) (exact erf GELU), x [M, 2F] -> y [M, F].
+ * Replaces the chunk + F.gelu + multiply of diffusers' GEGLU inside `model.ff`
+ * (i2vgen-xl/pnp_utils.py:335).  F % 8 == 0.
+ */
+int mvoc_geglu(const void* x, void* y, int64_t M, int F, int dtype, void* stream);
 
 /*
  * Latent compositing ("noise fusion") fused with the UNet input concat.

@@ -39,6 +39,20 @@ SIGNATURES = {
         c_int,
         [c_void_p] * 4 + [c_int64, c_int, c_int, c_int] + [c_int64] * 12 + [c_float, c_int, c_void_p],
     ),
+    "mvoc_attn_temporal_strided_fwd": (
+        c_int,
+        [c_void_p] * 4 + [c_int64, c_int64, c_int, c_int, c_int, ctypes.POINTER(c_int64), c_float, c_int, c_void_p],
+    ),
+    "mvoc_groupnorm_nhwc_partial_count": (c_int64, [c_int64, c_int]),
+    "mvoc_groupnorm_nhwc_geometry": (
+        c_int, [c_int64, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int64)]),
+    "mvoc_groupnorm_nhwc_stats": (
+        c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
+    "mvoc_groupnorm_nhwc_finalize": (
+        c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "mvoc_groupnorm_nhwc_apply": (
+        c_int, [c_void_p] * 6 + [c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "mvoc_geglu": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "mvoc_qk_blend": (
         c_int,
         [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_void_p],

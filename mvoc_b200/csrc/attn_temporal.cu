@@ -49,9 +49,11 @@ __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 12
 struct TAParams {
     const __nv_bfloat16 *q, *k, *v;
     __nv_bfloat16* o;
-    int64_t P;
+    int64_t P;        // problems = P_outer * P_inner
+    int64_t P_inner;  // problem index = outer * P_inner + inner
     int H;
-    int64_t q_sp, q_st, q_sh, k_sp, k_st, k_sh, v_sp, v_st, v_sh, o_sp, o_st, o_sh;
+    // element strides: (outer problem, inner problem, token, head) per tensor
+    int64_t q_so, q_sp, q_st, q_sh, k_so, k_sp, k_st, k_sh, v_so, v_sp, v_st, v_sh, o_so, o_sp, o_st, o_sh;
     float scale_log2;
 };
 
@@ -70,9 +72,10 @@ __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal_kernel(TAParams p
     const int h = (int)(item % p.H);
     const uint32_t sQ = smem_u32(ta_smem) + warp * 3 * TILE, sK = sQ + TILE, sV = sK + TILE;
 
-    const __nv_bfloat16* gq = p.q + prob * p.q_sp + (int64_t)h * p.q_sh;
-    const __nv_bfloat16* gk = p.k + prob * p.k_sp + (int64_t)h * p.k_sh;
-    const __nv_bfloat16* gv = p.v + prob * p.v_sp + (int64_t)h * p.v_sh;
+    const int64_t po = prob / p.P_inner, pi = prob - po * p.P_inner;
+    const __nv_bfloat16* gq = p.q + po * p.q_so + pi * p.q_sp + (int64_t)h * p.q_sh;
+    const __nv_bfloat16* gk = p.k + po * p.k_so + pi * p.k_sp + (int64_t)h * p.k_sh;
+    const __nv_bfloat16* gv = p.v + po * p.v_so + pi * p.v_sp + (int64_t)h * p.v_sh;
 #pragma unroll
     for (int i = 0; i < (T * 8) / 32; ++i) {
         const int idx = lane + 32 * i, r = idx >> 3, c = idx & 7;
@@ -96,7 +99,7 @@ __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal_kernel(TAParams p
 
     const int g = lane >> 2, t = lane & 3;
     const int mat = lane >> 3, mr = lane & 7;
-    __nv_bfloat16* go = p.o + prob * p.o_sp + (int64_t)h * p.o_sh;
+    __nv_bfloat16* go = p.o + po * p.o_so + pi * p.o_sp + (int64_t)h * p.o_sh;
 
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
@@ -209,27 +212,21 @@ static int ta_launch(const TAParams& p, cudaStream_t s) {
 
 using namespace mvoc;
 
-extern "C" int mvoc_attn_temporal_fwd(const void* q, const void* k, const void* v, void* o,
-                                      int64_t P, int T, int H, int D, int64_t q_sp, int64_t q_st,
-                                      int64_t q_sh, int64_t k_sp, int64_t k_st, int64_t k_sh,
-                                      int64_t v_sp, int64_t v_st, int64_t v_sh, int64_t o_sp,
-                                      int64_t o_st, int64_t o_sh, float scale, int dtype,
-                                      void* stream) {
-    MVOC_REQUIRE(q && k && v && o, MVOC_ERR_INVALID_ARG, "mvoc_attn_temporal_fwd: null pointer");
-    MVOC_REQUIRE(dtype == MVOC_BF16, MVOC_ERR_UNSUPPORTED,
-                 "mvoc_attn_temporal_fwd: dtype %d unsupported (bf16 only)", dtype);
-    MVOC_REQUIRE(D == 64, MVOC_ERR_UNSUPPORTED, "mvoc_attn_temporal_fwd: head_dim %d unsupported (64 only)", D);
-    MVOC_REQUIRE(P >= 0 && H > 0, MVOC_ERR_INVALID_ARG, "mvoc_attn_temporal_fwd: bad P/H");
-    MVOC_REQUIRE(P * H < ((int64_t)1 << 31) * TA_WARPS, MVOC_ERR_UNSUPPORTED,
-                 "mvoc_attn_temporal_fwd: too many problems");
-    const int64_t strides[12] = {q_sp, q_st, q_sh, k_sp, k_st, k_sh, v_sp, v_st, v_sh, o_sp, o_st, o_sh};
-    for (int i = 0; i < 12; ++i)
-        MVOC_REQUIRE(strides[i] % 8 == 0, MVOC_ERR_UNSUPPORTED,
-                     "mvoc_attn_temporal_fwd: stride #%d = %lld is not a multiple of 8 elements", i,
-                     (long long)strides[i]);
+static int ta_dispatch(const char* name, const void* q, const void* k, const void* v, void* o,
+                       int64_t P_outer, int64_t P_inner, int T, int H, int D, const int64_t* st /*[16]*/,
+                       float scale, int dtype, void* stream) {
+    MVOC_REQUIRE(q && k && v && o, MVOC_ERR_INVALID_ARG, "%s: null pointer", name);
+    MVOC_REQUIRE(dtype == MVOC_BF16, MVOC_ERR_UNSUPPORTED, "%s: dtype %d unsupported (bf16 only)", name, dtype);
+    MVOC_REQUIRE(D == 64, MVOC_ERR_UNSUPPORTED, "%s: head_dim %d unsupported (64 only)", name, D);
+    MVOC_REQUIRE(P_outer >= 0 && P_inner > 0 && H > 0, MVOC_ERR_INVALID_ARG, "%s: bad P/H", name);
+    const int64_t P = P_outer * P_inner;
+    MVOC_REQUIRE(P * H < ((int64_t)1 << 31) * TA_WARPS, MVOC_ERR_UNSUPPORTED, "%s: too many problems", name);
+    for (int i = 0; i < 16; ++i)
+        MVOC_REQUIRE(st[i] % 8 == 0, MVOC_ERR_UNSUPPORTED,
+                     "%s: stride #%d = %lld is not a multiple of 8 elements", name, i, (long long)st[i]);
     MVOC_REQUIRE(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) &&
                      ((uintptr_t)o % 16 == 0),
-                 MVOC_ERR_INVALID_ARG, "mvoc_attn_temporal_fwd: pointers must be 16-byte aligned");
+                 MVOC_ERR_INVALID_ARG, "%s: pointers must be 16-byte aligned", name);
     if (P == 0) return MVOC_OK;
     TAParams p;
     p.q = (const __nv_bfloat16*)q;
@@ -237,11 +234,12 @@ extern "C" int mvoc_attn_temporal_fwd(const void* q, const void* k, const void* 
     p.v = (const __nv_bfloat16*)v;
     p.o = (__nv_bfloat16*)o;
     p.P = P;
+    p.P_inner = P_inner;
     p.H = H;
-    p.q_sp = q_sp; p.q_st = q_st; p.q_sh = q_sh;
-    p.k_sp = k_sp; p.k_st = k_st; p.k_sh = k_sh;
-    p.v_sp = v_sp; p.v_st = v_st; p.v_sh = v_sh;
-    p.o_sp = o_sp; p.o_st = o_st; p.o_sh = o_sh;
+    p.q_so = st[0]; p.q_sp = st[1]; p.q_st = st[2]; p.q_sh = st[3];
+    p.k_so = st[4]; p.k_sp = st[5]; p.k_st = st[6]; p.k_sh = st[7];
+    p.v_so = st[8]; p.v_sp = st[9]; p.v_st = st[10]; p.v_sh = st[11];
+    p.o_so = st[12]; p.o_sp = st[13]; p.o_st = st[14]; p.o_sh = st[15];
     p.scale_log2 = scale * 1.4426950408889634f;
     cudaStream_t s = (cudaStream_t)stream;
     switch (T) {
@@ -250,7 +248,27 @@ extern "C" int mvoc_attn_temporal_fwd(const void* q, const void* k, const void* 
         case 24: return ta_launch<24>(p, s);
         case 32: return ta_launch<32>(p, s);
         default:
-            set_error("mvoc_attn_temporal_fwd: T=%d unsupported (8, 16, 24 or 32 frames)", T);
+            set_error("%s: T=%d unsupported (8, 16, 24 or 32 frames)", name, T);
             return MVOC_ERR_UNSUPPORTED;
     }
+}
+
+extern "C" int mvoc_attn_temporal_fwd(const void* q, const void* k, const void* v, void* o,
+                                      int64_t P, int T, int H, int D, int64_t q_sp, int64_t q_st,
+                                      int64_t q_sh, int64_t k_sp, int64_t k_st, int64_t k_sh,
+                                      int64_t v_sp, int64_t v_st, int64_t v_sh, int64_t o_sp,
+                                      int64_t o_st, int64_t o_sh, float scale, int dtype,
+                                      void* stream) {
+    const int64_t st[16] = {0, q_sp, q_st, q_sh, 0, k_sp, k_st, k_sh, 0, v_sp, v_st, v_sh, 0, o_sp, o_st, o_sh};
+    return ta_dispatch("mvoc_attn_temporal_fwd", q, k, v, o, P > 0 ? 1 : 0, P > 0 ? P : 1, T, H, D, st,
+                       scale, dtype, stream);
+}
+
+extern "C" int mvoc_attn_temporal_strided_fwd(const void* q, const void* k, const void* v, void* o,
+                                              int64_t P_outer, int64_t P_inner, int T, int H, int D,
+                                              const int64_t* strides16, float scale, int dtype,
+                                              void* stream) {
+    MVOC_REQUIRE(strides16 != nullptr, MVOC_ERR_INVALID_ARG, "mvoc_attn_temporal_strided_fwd: null strides");
+    return ta_dispatch("mvoc_attn_temporal_strided_fwd", q, k, v, o, P_outer, P_inner, T, H, D, strides16,
+                       scale, dtype, stream);
 }

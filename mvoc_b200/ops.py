@@ -314,3 +314,123 @@ def ddim_inverse_step_(pred_uncond: torch.Tensor, pred_cond: Optional[torch.Tens
                                     _dt(pred_uncond), _dt(x), _stream())
     _cabi.check(st, "mvoc_ddim_inverse_step")
     _count()
+
+
+# --------------------------------------------------------------------------
+# channels-last (NHWC) path
+# --------------------------------------------------------------------------
+_gnh_geom: dict = {}
+_gnh_bufs: dict = {}
+
+
+def _gnh_geometry(S: int, C: int, dt: int):
+    key = (S, C, dt)
+    g = _gnh_geom.get(key)
+    if g is None:
+        import ctypes
+
+        chunks, tpc = ctypes.c_int(0), ctypes.c_int64(0)
+        _cabi.check(_cabi.load().mvoc_groupnorm_nhwc_geometry(S, C, dt, ctypes.byref(chunks), ctypes.byref(tpc)),
+                    "mvoc_groupnorm_nhwc_geometry")
+        g = (chunks.value, tpc.value)
+        _gnh_geom[key] = g
+    return g
+
+
+def groupnorm_nhwc(
+    x: torch.Tensor,
+    weight: torch.Tensor,
+    bias: torch.Tensor,
+    groups: int,
+    eps: float,
+    silu: bool,
+    frames_per_stat: int = 1,
+    add: Optional[torch.Tensor] = None,
+    out: Optional[torch.Tensor] = None,
+    gather=None,
+) -> torch.Tensor:
+    """GroupNorm(+SiLU) over channels-last x [N, S, C] (or [N, H, W, C]); `add` [N, C] is added to x first
+    (the resnet time embedding).  `gather(partial [N,G,chunks,2]) -> [sets,N,G,chunks,2]` merges the
+    statistics of pixel shards living on other GPUs (mvoc_b200.parallel); None on a single GPU."""
+    _need_cuda(x, weight, bias, add, out)
+    if not x.is_contiguous():
+        raise ValueError("groupnorm_nhwc: x must be contiguous [N, ..., C]")
+    N, C = x.shape[0], x.shape[-1]
+    S = x.numel() // (N * C)
+    if out is None:
+        out = torch.empty_like(x)
+    if add is not None and (tuple(add.shape) != (N, C) or not add.is_contiguous() or add.dtype != x.dtype):
+        raise ValueError(f"groupnorm_nhwc: add must be contiguous [{N}, {C}] of x's dtype")
+    dt = _dt(x)
+    lib = _cabi.load()
+    chunks, tpc = _gnh_geometry(S, C, dt)
+    partial = torch.empty((N, groups, chunks, 2), dtype=torch.float32, device=x.device)
+    with _Timed(("groupnorm", N, C, S, frames_per_stat), 2.0 * x.numel() * x.element_size()):
+        _cabi.check(lib.mvoc_groupnorm_nhwc_stats(x.data_ptr(), _ptr(add), partial.data_ptr(), N, S, C, groups, dt,
+                                                  _stream()), "mvoc_groupnorm_nhwc_stats")
+        sets = 1
+        if gather is not None:
+            partial = gather(partial)
+            sets = partial.shape[0]
+        ckey = (x.device.index, S, C, groups, sets)
+        counts = _gnh_bufs.get(ckey)
+        if counts is None:
+            cg = C // groups
+            per = [float(max(0, min(S, (c + 1) * tpc) - c * tpc) * cg) for c in range(chunks)]
+            counts = torch.tensor(per * sets, dtype=torch.float32, device=x.device)
+            _gnh_bufs[ckey] = counts
+        stat = torch.empty((N // frames_per_stat, groups, 2), dtype=torch.float32, device=x.device)
+        _cabi.check(lib.mvoc_groupnorm_nhwc_finalize(partial.data_ptr(), counts.data_ptr(), stat.data_ptr(), N, groups,
+                                                     chunks, frames_per_stat, sets, float(eps), _stream()),
+                    "mvoc_groupnorm_nhwc_finalize")
+        _cabi.check(lib.mvoc_groupnorm_nhwc_apply(x.data_ptr(), out.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                                                  _ptr(add), stat.data_ptr(), N, S, C, groups, frames_per_stat,
+                                                  int(bool(silu)), dt, _stream()), "mvoc_groupnorm_nhwc_apply")
+    _count(3)
+    return out
+
+
+def geglu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [..., 2F] -> x[..., :F] * gelu(x[..., F:]) in one pass."""
+    _need_cuda(x, out)
+    if not x.is_contiguous():
+        raise ValueError("geglu: x must be contiguous")
+    F2 = x.shape[-1]
+    F = F2 // 2
+    M = x.numel() // F2
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (F,), dtype=x.dtype, device=x.device)
+    with _Timed(("geglu", M, F), 3.0 * M * F * x.element_size()):
+        _cabi.check(_cabi.load().mvoc_geglu(x.data_ptr(), out.data_ptr(), M, F, _dt(x), _stream()), "mvoc_geglu")
+    _count()
+    return out
+
+
+def temporal_attention_frames(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, B: int, T: int,
+                              S: int, scale: Optional[float] = None, out: Optional[torch.Tensor] = None):
+    """Attention over the T frames of every (video, pixel) for row-major tokens in (b, t, pixel) order.
+    q, k, v: [B*T*S, H*64] 2-D views (row stride arbitrary, e.g. slices of a fused QKV GEMM output);
+    returns [B*T*S, H*64] in the same order — no (b t) <-> (b hw) permute is materialised."""
+    import ctypes
+
+    _need_cuda(q, k, v, out)
+    C = heads * HEAD_DIM
+    rows = B * T * S
+    for t in (q, k, v):
+        if t.dim() != 2 or t.shape[0] != rows or t.shape[1] != C or t.stride(1) != 1:
+            raise ValueError(f"temporal_attention_frames: expected [{rows}, {C}] row-major views, got {tuple(t.shape)}")
+    if out is None:
+        out = torch.empty((rows, C), dtype=q.dtype, device=q.device)
+    if scale is None:
+        scale = HEAD_DIM ** -0.5
+    st = []
+    for t in (q, k, v, out):
+        rs = t.stride(0)
+        st += [T * S * rs, rs, S * rs, HEAD_DIM]
+    arr = (ctypes.c_int64 * 16)(*st)
+    with _Timed(("attn_temporal", B * S, heads, T), 4.0 * rows * C * q.element_size()):
+        rc = _cabi.load().mvoc_attn_temporal_strided_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                                        B, S, T, heads, HEAD_DIM, arr, float(scale), _dt(q), _stream())
+    _cabi.check(rc, "mvoc_attn_temporal_strided_fwd")
+    _count()
+    return out

@@ -57,12 +57,77 @@ class FrameParallel:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
         return float(t.item())
 
-    # ------------------------------------------------------------------ frame sharding
-    def frame_slice(self, n_frames: int) -> slice:
+    # ------------------------------------------------------------------ shard geometry
+    def frame_range(self, n_frames: int):
+        """(lo, hi) of the frames this rank owns."""
         if n_frames % self.world != 0:
             raise ValueError(f"n_frames={n_frames} is not divisible by world_size={self.world}")
         per = n_frames // self.world
-        return slice(self.rank * per, (self.rank + 1) * per)
+        return (self.rank * per, (self.rank + 1) * per)
 
-    def local_frames(self, n_frames: int) -> int:
-        return n_frames // self.world if self.world > 1 else n_frames
+    def pixel_range(self, n_pixels: int):
+        """(lo, hi) of the pixels this rank owns while a temporal operator runs."""
+        if n_pixels % self.world != 0:
+            raise ValueError(f"h*w={n_pixels} is not divisible by world_size={self.world}")
+        per = n_pixels // self.world
+        return (self.rank * per, (self.rank + 1) * per)
+
+    # ------------------------------------------------------------------ re-layout (the exchange step)
+    def to_pixel_shards(self, x: torch.Tensor, num_frames: int) -> torch.Tensor:
+        """[(b t_local), h, w, C] (this rank's frames, all pixels) -> [(b T), 1, S/P, C] (all frames, this
+        rank's pixels): one all-to-all.  Rows stay in (video, frame, pixel) order."""
+        P = self.world
+        btl, h, w, C = x.shape
+        tl = num_frames // P
+        b, S = btl // tl, h * w
+        sp = S // P
+        if S % P != 0:
+            raise ValueError(f"h*w={S} is not divisible by world_size={P}")
+        send = x.view(b, tl, P, sp, C).permute(2, 0, 1, 3, 4).contiguous()       # [dst, b, tl, sp, C]
+        recv = torch.empty_like(send)                                            # [src, b, tl, sp, C]
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv.permute(1, 0, 2, 3, 4).reshape(b * num_frames, 1, sp, C)     # frame = src*tl + i
+
+    def to_frame_shards(self, y: torch.Tensor, num_frames: int, h: int, w: int) -> torch.Tensor:
+        """Inverse of to_pixel_shards: [(b T), 1, S/P, C] -> [(b t_local), h, w, C]."""
+        P = self.world
+        bT, _, sp, C = y.shape
+        b, tl = bT // num_frames, num_frames // P
+        send = y.view(b, P, tl, sp, C).permute(1, 0, 2, 3, 4).contiguous()       # [dst(frame owner), b, tl, sp, C]
+        recv = torch.empty_like(send)                                            # [src(pixel owner), b, tl, sp, C]
+        dist.all_to_all_single(recv, send, group=self.group)
+        return recv.permute(1, 2, 0, 3, 4).reshape(b * tl, h, w, C)              # pixel = src*sp + j
+
+    def gather_partials(self, partial: torch.Tensor) -> torch.Tensor:
+        """GroupNorm partial statistics of every rank's pixel shard: [N,G,chunks,2] -> [P,N,G,chunks,2]."""
+        partial = partial.contiguous()
+        out = torch.empty((self.world * partial.shape[0],) + tuple(partial.shape[1:]), dtype=partial.dtype,
+                          device=partial.device)
+        dist.all_gather_into_tensor(out, partial, group=self.group)   # concatenated along dim 0
+        return out.view((self.world,) + tuple(partial.shape))
+
+    def gather_frames(self, x: torch.Tensor) -> torch.Tensor:
+        """[k, t_local, ...] on every rank -> [k, T, ...] (frames in rank order)."""
+        x = x.contiguous()
+        out = torch.empty((self.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x, group=self.group)
+        out = out.view((self.world,) + tuple(x.shape))
+        k, tl = x.shape[0], x.shape[1]
+        return out.permute(1, 0, 2, *range(3, out.dim())).reshape(k, self.world * tl, *x.shape[2:])
+
+    # ------------------------------------------------------------------ temporal operators on pixel shards
+    def temporal_transformer(self, module, hidden_states: torch.Tensor, num_frames: int) -> torch.Tensor:
+        _, h, w, _ = hidden_states.shape
+        xs = self.to_pixel_shards(hidden_states, num_frames)
+        module.ctx.full_hw = (h, w)
+        try:
+            ys = module.forward_local(xs, num_frames, self.gather_partials)
+        finally:
+            module.ctx.full_hw = None
+        return self.to_frame_shards(ys, num_frames, h, w)
+
+    def temporal_conv(self, module, hidden_states: torch.Tensor, num_frames: int) -> torch.Tensor:
+        _, h, w, _ = hidden_states.shape
+        xs = self.to_pixel_shards(hidden_states, num_frames)
+        ys = module.forward_local(xs, num_frames, self.gather_partials)
+        return self.to_frame_shards(ys, num_frames, h, w)

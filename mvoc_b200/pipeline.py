@@ -91,30 +91,39 @@ class I2VGenXLPipeline:
 
     # ------------------------------------------------------------------ UNet driver
     def _unet_forward(self, sample, t: int, cond: Conditioning):
-        """I2VGenXLUnetExtension.forward (pipeline_i2vgen_xl.py:109-362).  The context tokens and the
-        image-latent stem input do not depend on t, so they are computed on the first step only."""
+        """I2VGenXLUnetExtension.forward (pipeline_i2vgen_xl.py:109-362) -> noise prediction of THIS rank's
+        frames, [b, t_local, 4, h, w].  The context tokens and the image-latent stem input do not depend on
+        t, so they are computed on the first step only (the reference recomputes them every step, T times).
+        With world_size > 1 every rank runs all branches on its T/P frames (frame-parallel)."""
         unet = self.unet
+        par = self.parallel
+        unet.ctx.parallel = par if par.world > 1 else None
         b, c, T, h, w = sample.shape
+        f0, f1 = par.frame_range(T) if par.world > 1 else (0, T)
+        tl = f1 - f0
         cache = self._cond_cache
         if cache is None or cache["key"] is not cond:
             ctx = unet.context(cond.prompt_embeds, cond.image_latents, cond.image_embeddings)
-            ctx = ctx.repeat_interleave(T, dim=0)                               # one context per frame (:255-260)
-            il = cond.image_latents_first.permute(0, 2, 1, 3, 4).reshape(b * T, c, h, w)
-            il = unet.image_latents_proj_in(il)
-            il = il.view(b, T, c, h, w).permute(0, 3, 4, 1, 2).reshape(b * h * w, T, c)
-            il = unet.image_latents_temporal_encoder(il)
-            il = il.reshape(b, h, w, T, c).permute(0, 3, 4, 1, 2).reshape(b * T, c, h, w).contiguous()
+            ctx = ctx.repeat_interleave(tl, dim=0)                              # one context per frame (:255-260)
+            il = unet.stem_condition(cond.image_latents_first)                 # [(b T), c, h, w]
+            il = il.view(b, T, c, h, w)[:, f0:f1].reshape(b * tl, c, h, w).contiguous()
             fps_emb = unet.fps_embedding(unet.time_proj(cond.fps).to(unet.dtype))
             cache = {"key": cond, "ctx": ctx, "il": il, "fps_emb": fps_emb}
             self._cond_cache = cache
         ts = torch.full((b,), int(t), dtype=torch.int64, device=sample.device)
         t_emb = unet.time_embedding(unet.time_proj(ts).to(unet.dtype))
-        emb = (t_emb + cache["fps_emb"]).repeat_interleave(T, dim=0)             # :196-197
-        x = torch.cat([sample.permute(0, 2, 1, 3, 4).reshape(b * T, c, h, w), cache["il"]], dim=1)  # :282-283
-        x = unet.conv_in(x)
-        x = unet.transformer_in(x, num_frames=T)[0]
+        emb = (t_emb + cache["fps_emb"]).repeat_interleave(tl, dim=0)            # :196-197
+        frames = sample[:, :, f0:f1].permute(0, 2, 1, 3, 4).reshape(b * tl, c, h, w)   # :283
+        x = unet.stem(frames, cache["il"], T)                                   # :282-290
         fwd_up = any(s % (2 ** unet.num_upsamplers) != 0 for s in (h, w))
-        return unet.body(x, emb, cache["ctx"], T, fwd_up)
+        out = unet.body(x, emb, cache["ctx"], T, fwd_up)                        # [(b t_local), 4, h, w]
+        return out.view(b, tl, *out.shape[1:])
+
+    def _gather_prediction(self, pred_local: torch.Tensor) -> torch.Tensor:
+        """[k, t_local, 4, h, w] -> [k, 4, T, h, w] contiguous (the latents' layout)."""
+        if self.parallel.world > 1:
+            pred_local = self.parallel.gather_frames(pred_local)
+        return pred_local.permute(0, 2, 1, 3, 4).contiguous()
 
     # ------------------------------------------------------------------ composition
     @torch.no_grad()
@@ -178,7 +187,7 @@ class I2VGenXLPipeline:
                                   random_noise_ratio, do_fusion, obj_random_noise_fusion)
             pnp_utils.register_time_all(self, t, masks)                          # :1684-1685
             noise_pred = self._unet_forward(unet_in, t, cond)                   # :1688-1699
-            pred = noise_pred[n_obj + 1:].contiguous()                          # uncond, cond (:1714-1715)
+            pred = self._gather_prediction(noise_pred[n_obj + 1:])              # uncond, cond (:1714-1715)
             a_t, a_prev = sched.step_alphas(t)
             ops.cfg_ddim_step_(pred[0], pred[1], latents, guidance_scale, a_t, a_prev)  # :1717-1731
             if host_io:
@@ -214,7 +223,7 @@ class I2VGenXLPipeline:
             if max_steps is not None and i >= max_steps:
                 break
             noise_pred = self._unet_forward(x.to(self.unet.dtype), t, cond)     # :1952-1961
-            pred = noise_pred.contiguous()
+            pred = self._gather_prediction(noise_pred)
             a_src, a_dst = sched.step_alphas(t)
             ops.ddim_inverse_step_(pred, None, x, 1.0, a_src, a_dst)            # :1979
             if keep:

@@ -26,7 +26,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .unet3d import AttnProcessor2_0, _run_attention
+from .unet3d import AttnProcessor2_0, run_attention
 
 MaskPair = Tuple[torch.Tensor, torch.Tensor]
 
@@ -37,49 +37,46 @@ MaskPair = Tuple[torch.Tensor, torch.Tensor]
 class _MaskCache:
     """The reference re-materialises a [T,h,w,C] mask per object per layer per step
     (pnp_utils.py:648-656, :805-809).  The kernels read one value per token, so the nearest-resized,
-    token-ordered masks are built once per (mask list, resolution, mode) and reused."""
+    token-ordered masks are built once per (mask list, resolution, kind, shard) and reused.
+    Token order is (frame, pixel) everywhere — the row order of the channels-last activations."""
 
     def __init__(self):
         self._store = {}
 
     @staticmethod
-    def _key(mask: Sequence[MaskPair], kind: str, h: int, w: int):
-        return (kind, h, w) + tuple((m[0].data_ptr(), m[1].data_ptr(), m[0]._version, m[1]._version) for m in mask)
+    def _key(mask: Sequence[MaskPair], *extra):
+        return extra + tuple((m[0].data_ptr(), m[1].data_ptr(), m[0]._version, m[1]._version) for m in mask)
 
-    def spatial_tokens(self, mask, h, w) -> torch.Tensor:
-        """[n_obj, T*h*w] uint8, (frame, pixel) order, from the BINARY masks (pnp_utils.py:648-651)."""
-        key = self._key(mask, "spa", h, w)
+    def tokens(self, mask, h, w, soft: bool, frames=None, pixels=None) -> torch.Tensor:
+        """[n_obj, T'*S'] in (frame, pixel) order.  soft=False: uint8 from the BINARY masks
+        (pnp_utils.py:648-651, :986-994); soft=True: float32 from the FLOAT masks (:805-809).  Both are
+        nearest-resized from the latent resolution to (h, w); `frames` / `pixels` = (lo, hi) shard ranges."""
+        key = self._key(mask, "soft" if soft else "bin", h, w, frames, pixels)
         out = self._store.get(key)
         if out is None:
             rows = []
-            for _, mb in mask:
-                m = mb[0].to(torch.float32)                       # [4,T,H,W]  ("a b l h w -> (a b) l h w")
-                m = F.interpolate(m, size=(h, w), mode="nearest")[0]  # channel 0: [T,h,w]
-                rows.append((m != 0).to(torch.uint8).reshape(-1))
+            for mf, mb in mask:
+                m = (mf if soft else mb)[0].to(torch.float32)            # [4,T,H,W]
+                m = F.interpolate(m, size=(h, w), mode="nearest")[0]      # channel 0: [T,h,w]
+                m = m.reshape(m.shape[0], h * w)
+                if frames is not None:
+                    m = m[frames[0]:frames[1]]
+                if pixels is not None:
+                    m = m[:, pixels[0]:pixels[1]]
+                rows.append(m.reshape(-1) if soft else (m != 0).to(torch.uint8).reshape(-1))
             out = torch.stack(rows).contiguous()
             self._store[key] = out
         return out
 
-    def temporal_tokens(self, mask, h, w) -> torch.Tensor:
-        """[n_obj, h*w*T] float32, (pixel, frame) order, from the FLOAT masks (pnp_utils.py:805-809)."""
-        key = self._key(mask, "tmp", h, w)
+    def feature_planes(self, mask, frames=None) -> torch.Tensor:
+        """[n_obj, T', H*W] uint8 from the BINARY masks at full latent resolution (pnp_utils.py:986-994)."""
+        key = self._key(mask, "feat", frames)
         out = self._store.get(key)
         if out is None:
-            rows = []
-            for mf, _ in mask:
-                m = mf[0].to(torch.float32)                       # squeeze(0): [4,T,H,W]
-                m = F.interpolate(m, size=(h, w), mode="nearest")[0]  # [T,h,w]
-                rows.append(m.permute(1, 2, 0).reshape(-1))
-            out = torch.stack(rows).contiguous()
-            self._store[key] = out
-        return out
-
-    def feature_planes(self, mask) -> torch.Tensor:
-        """[n_obj, T, H*W] uint8 from the BINARY masks at full latent resolution (pnp_utils.py:986-994)."""
-        key = self._key(mask, "feat", 0, 0)
-        out = self._store.get(key)
-        if out is None:
-            out = torch.stack([mb[0, 0].reshape(mb.shape[2], -1).to(torch.uint8) for _, mb in mask]).contiguous()
+            planes = [mb[0, 0].reshape(mb.shape[2], -1).to(torch.uint8) for _, mb in mask]
+            if frames is not None:
+                planes = [p_[frames[0]:frames[1]] for p_ in planes]
+            out = torch.stack(planes).contiguous()
             self._store[key] = out
         return out
 
@@ -102,6 +99,12 @@ def _fires(obj) -> bool:
     return t in cached[1] or t == 1000
 
 
+def _partition(module):
+    ctx = getattr(module, "ctx", None)
+    par = ctx.parallel if ctx is not None else None
+    return par if (par is not None and par.world > 1) else None
+
+
 # --------------------------------------------------------------------------
 # processors
 # --------------------------------------------------------------------------
@@ -110,6 +113,8 @@ class _InjectingProcessor(AttnProcessor2_0):
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None,
                  height=None, width=None, scale: float = 1.0):
+        """hidden_states: [n_branches * T', S', C] channels-last tokens, frames outermost inside a branch
+        (spatial: T' = this rank's frames, S' = h*w; temporal: T' = all frames, S' = this rank's pixels)."""
         if encoder_hidden_states is not None or not _fires(self):
             return super().__call__(attn, hidden_states, encoder_hidden_states, attention_mask, temb, scale)
         mask = self.mask
@@ -121,12 +126,19 @@ class _InjectingProcessor(AttnProcessor2_0):
         q = attn.to_q(hidden_states)                                            # :604
         k = attn.to_k(hidden_states)                                            # :611
         v = attn.to_v(hidden_states)                                            # :612
+        par = _partition(attn)
+        n_frames_total = mask[0][0].shape[2]
         if self.temporal:
-            tokens = _MASKS.temporal_tokens(mask, height, width)
+            if par is not None:   # rows are this rank's pixel shard of the (fh x fw) frame
+                fh, fw = attn.ctx.full_hw
+                tokens = _MASKS.tokens(mask, fh, fw, soft=True, pixels=par.pixel_range(fh * fw))
+            else:
+                tokens = _MASKS.tokens(mask, height, width, soft=True)           # float mask (:805)
         else:
-            tokens = _MASKS.spatial_tokens(mask, height, width)
+            frm = par.frame_range(n_frames_total) if par is not None else None
+            tokens = _MASKS.tokens(mask, height, width, soft=False, frames=frm)  # binary mask (:648)
         ops.qk_blend_(q, k, tokens, n_obj, bool(self.inject_background))         # :628-672 / :782-850
-        out = _run_attention(q, k, v, attn.heads)                               # :684 / :862
+        out = run_attention(q, k, v, attn.heads, attn.temporal)                  # :684 / :862
         return attn.to_out[0](out)                                              # :692
 
 
@@ -174,7 +186,8 @@ def injected_attention_sites(unet):
 # --------------------------------------------------------------------------
 def _feature_hook(module, hidden_states):
     """Blend of the composite slots from the background slot + objects, in place
-    (pnp_utils.py:970-1004 / :1059-1082 / :1114-1146)."""
+    (pnp_utils.py:970-1004 / :1059-1082 / :1114-1146).  hidden_states is channels-last
+    [n_branches*T', H, W, C] (resnet / temporal conv) or NCHW [n_branches*T', 4, H, W] (conv_out)."""
     if not _fires(module):
         return
     mask = module.mask
@@ -183,7 +196,15 @@ def _feature_hook(module, hidden_states):
     if hidden_states.shape[0] % nb != 0:
         raise ValueError(f"batch {hidden_states.shape[0]} is not divisible into n_obj+3={nb} branches")
     frames = hidden_states.shape[0] // nb
-    ops.feature_blend_(hidden_states, _MASKS.feature_planes(mask), n_obj, frames)
+    n_frames_total = mask[0][0].shape[2]
+    par = _partition(module)
+    frm = par.frame_range(n_frames_total) if par is not None else None
+    if getattr(module, "feature_layout", "nhwc") == "nchw":
+        ops.feature_blend_(hidden_states, _MASKS.feature_planes(mask, frm), n_obj, frames)
+    else:
+        H, W = hidden_states.shape[1], hidden_states.shape[2]
+        # a binary-mask blend of channels-last rows is the same select as the Q/K blend with base = slot 0
+        ops.qk_blend_(hidden_states, None, _MASKS.tokens(mask, H, W, soft=False, frames=frm), n_obj, True)
 
 
 def register_resnet_injection(model, injection_schedule):
@@ -203,6 +224,8 @@ def register_temp_conv_injection(model, injection_schedule):
 def register_out_conv_injection(model, injection_schedule):
     m = model.unet.conv_out                 # pnp_utils.py:1157
     m.feature_hook = _feature_hook
+    m.feature_layout = "nchw"               # 4 channels: blended after the cast back to [N,4,H,W]
+    m.ctx = model.unet.ctx
     setattr(m, "injection_schedule", injection_schedule)
 
 

@@ -6,9 +6,17 @@ objects — ``unet.up_blocks[i].attentions[j].transformer_blocks[0].attn1.proces
 checkpoint's state dict loads unchanged.
 
 What runs underneath is this repo's C-ABI library (``mvoc_b200.ops``): every attention
-(tcgen05 flash attention / warp-per-pixel temporal attention), every GroupNorm(+SiLU), the mask
-blends and the latent/DDIM updates are sm_100a kernels.  Dense GEMMs / convolutions stay on
-cuBLAS / cuDNN through torch.  There is no CPU path: tensors must be CUDA.
+(tcgen05 flash attention / warp-per-pixel temporal attention), every GroupNorm(+SiLU), the GEGLU
+gate, the mask blends and the latent/DDIM updates are sm_100a kernels.  Dense GEMMs / convolutions
+stay on cuBLAS / cuDNN through torch.  There is no CPU path: tensors must be CUDA.
+
+Data layout: activations are channels-last ``[B*T, H, W, C]`` (frames outermost) from conv_in to
+conv_out.  In that layout every 1x1 conv / Linear / LayerNorm is a row-wise op on ``[B*T*H*W, C]``,
+the spatial transformer's NCHW<->NLC permutes (pnp_utils.py:434, :502) are views, and the temporal
+transformer needs no ``[(b t) c h w] <-> [(b h w) t c]`` permute (pnp_utils.py:189, :207-213) at all:
+its row-wise ops do not care about row order and the temporal attention kernel walks the frames of a
+pixel with a stride.  The first NCHW version of this file spent ~40 % of a step in cuDNN
+nchw<->nhwc conversions and strided elementwise copies (profiles/r01_launches_v1_nchw_summary.txt).
 
 Forward bodies restate the functions MVOC re-points (i2vgen-xl/pnp_utils.py:170-548) and the stock
 diffusers blocks; citations are on each method.
@@ -68,11 +76,29 @@ class UNetConfig:
 
 
 # ------------------------------------------------------------------ small pieces
-class GroupNormAct(nn.GroupNorm):
-    """nn.GroupNorm parameters, executed by mvoc_groupnorm_silu (optionally fused SiLU and 5-D statistics)."""
+class _Ctx:
+    """Per-UNet execution context shared by its modules: the (optional) multi-GPU partition."""
 
-    def forward(self, x, silu: bool = False, frames_per_stat: int = 1, out=None):
-        return ops.groupnorm_silu(x, self.weight, self.bias, self.num_groups, self.eps, silu, frames_per_stat, out)
+    def __init__(self):
+        self.parallel = None   # mvoc_b200.parallel.FrameParallel or None
+        self.full_hw = None    # (h, w) of the un-sharded frame while a temporal operator runs on pixel shards
+
+
+def conv_nhwc(x: torch.Tensor, conv: nn.Conv2d, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """3x3 / strided conv on a channels-last activation [N, H, W, C] -> [N, H', W', C'] (cuDNN NHWC kernels:
+    the permuted view IS torch's channels_last memory format, so no nchw<->nhwc conversion runs)."""
+    y = F.conv2d(x.permute(0, 3, 1, 2), conv.weight, conv.bias if bias is None else bias, conv.stride, conv.padding)
+    y = y.permute(0, 2, 3, 1)
+    return y if y.is_contiguous() else y.contiguous()
+
+
+class GroupNormAct(nn.GroupNorm):
+    """nn.GroupNorm parameters, executed by the channels-last GroupNorm kernels (optionally fused SiLU,
+    fused per-(frame, channel) add, statistics over the T frames of a video)."""
+
+    def forward(self, x, silu: bool = False, frames_per_stat: int = 1, add=None, out=None, gather=None):
+        return ops.groupnorm_nhwc(x, self.weight, self.bias, self.num_groups, self.eps, silu, frames_per_stat,
+                                  add, out, gather)
 
 
 class Timesteps(nn.Module):
@@ -99,11 +125,26 @@ class TimestepEmbedding(nn.Module):
 
 
 # ------------------------------------------------------------------ attention
-def _run_attention(q, k, v, heads):
-    """Dispatch on sequence length: frames (<= 32 tokens) -> temporal kernel, else tcgen05 kernel."""
-    if q.shape[1] <= TEMPORAL_MAX_TOKENS and k.shape[1] == q.shape[1] and q.shape[1] % 8 == 0:
-        return ops.temporal_attention(q, k, v, heads)
-    return ops.attention(q, k, v, heads)
+class TemporalShape:
+    """Marks hidden_states [B*T, S, C] as frame-major tokens whose attention runs over the T frames of
+    each (video, pixel) — what the reference expresses by permuting to [(b h w), T, C] (pnp_utils.py:189)."""
+
+    __slots__ = ("videos", "frames", "pixels")
+
+    def __init__(self, videos: int, frames: int, pixels: int):
+        self.videos, self.frames, self.pixels = videos, frames, pixels
+
+
+def run_attention(q, k, v, heads, temporal: Optional[TemporalShape]):
+    """q [N, Sq, C], k/v [N, Sk, C] (any row stride).  Spatial / cross: tcgen05 kernel over the S axis.
+    Temporal: warp-per-(pixel, head) kernel over the frame axis, reading the frame-major rows in place."""
+    if temporal is None:
+        return ops.attention(q, k, v, heads)
+    C = q.shape[-1]
+    rows = q.shape[0] * q.shape[1]
+    o = ops.temporal_attention_frames(q.view(rows, C), k.view(rows, C), v.view(rows, C), heads,
+                                      temporal.videos, temporal.frames, temporal.pixels)
+    return o.view(q.shape[0], q.shape[1], C)
 
 
 class AttnProcessor2_0:
@@ -119,9 +160,8 @@ class AttnProcessor2_0:
         else:
             q = attn.to_q(hidden_states)
             k, v = attn.kv_cross(encoder_hidden_states)
-        out = _run_attention(q, k, v, attn.heads)
-        out = attn.to_out[0](out)
-        return out
+        out = run_attention(q, k, v, attn.heads, attn.temporal if encoder_hidden_states is None else None)
+        return attn.to_out[0](out)
 
 
 class Attention(nn.Module):
@@ -145,6 +185,8 @@ class Attention(nn.Module):
         self._accepts_hw = False
         self._w_qkv = None
         self._w_kv = None
+        self.temporal: Optional[TemporalShape] = None   # set per call by the temporal transformer
+        self.ctx: Optional[_Ctx] = None
         self.processor = AttnProcessor2_0()
 
     # `module.processor = obj` is how MVOC installs its processors (pnp_utils.py:715, :897)
@@ -190,8 +232,7 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
     def forward(self, x):
-        x, gate = self.proj(x).chunk(2, dim=-1)
-        return x * F.gelu(gate)
+        return ops.geglu(self.proj(x))      # x * gelu(gate) in one pass (mvoc_geglu)
 
 
 class GELU(nn.Module):
@@ -215,7 +256,8 @@ class FeedForward(nn.Module):
 
 
 class BasicTransformerBlock(nn.Module):
-    """basic_transformer_block_forward, pnp_utils.py:222-346 (norm_type 'layer_norm')."""
+    """basic_transformer_block_forward, pnp_utils.py:222-346 (norm_type 'layer_norm').  Row-wise except for
+    the two attention cores; `temporal` selects the frame axis for them."""
 
     def __init__(self, dim, num_attention_heads, attention_head_dim, cross_attention_dim=None,
                  double_self_attention=False):
@@ -230,7 +272,10 @@ class BasicTransformerBlock(nn.Module):
         self.norm3 = nn.LayerNorm(dim, eps=1e-5)
         self.ff = FeedForward(dim, activation_fn="geglu")
 
-    def forward(self, hidden_states, encoder_hidden_states=None, height=None, width=None):
+    def forward(self, hidden_states, encoder_hidden_states=None, height=None, width=None,
+                temporal: Optional[TemporalShape] = None):
+        self.attn1.temporal = temporal
+        self.attn2.temporal = temporal
         h = self.attn1(self.norm1(hidden_states), encoder_hidden_states=None, height=height, width=width)
         hidden_states = h.add_(hidden_states)                                   # :283
         h = self.attn2(self.norm2(hidden_states), encoder_hidden_states=encoder_hidden_states)
@@ -240,10 +285,9 @@ class BasicTransformerBlock(nn.Module):
 
 
 class Transformer2DModel(nn.Module):
-    """transformer2dmodel_forward live branch, pnp_utils.py:426-434 and :462-508.
-
-    proj_in (1x1 conv) + NCHW->NLC and NLC->NCHW + proj_out (1x1 conv) + residual are each ONE batched
-    GEMM on transposed views, so neither permute is materialised."""
+    """transformer2dmodel_forward live branch, pnp_utils.py:426-434 and :462-508, on channels-last
+    activations: the NCHW->NLC permute (:434) and its inverse (:502) are views and the two 1x1 convs are
+    row-wise GEMMs."""
 
     def __init__(self, num_attention_heads, attention_head_dim, in_channels, cross_attention_dim, norm_num_groups=32):
         super().__init__()
@@ -256,27 +300,19 @@ class Transformer2DModel(nn.Module):
         self.proj_out = nn.Conv2d(inner, in_channels, kernel_size=1)
 
     def forward(self, hidden_states, encoder_hidden_states=None, **kwargs):
-        batch, C, height, width = hidden_states.shape
-        hw = height * width
-        residual = hidden_states
-        x = self.norm(hidden_states)                                            # :430
+        n, height, width, C = hidden_states.shape
         inner = self.proj_in.out_channels
-        w_in = self.proj_in.weight.view(inner, C)
-        # [B, hw, C] (transposed view) @ [C, inner] + bias  ==  proj_in then permute(0,2,3,1)   :432-434
-        tokens = torch.baddbmm(self.proj_in.bias.view(1, 1, inner), x.view(batch, C, hw).transpose(1, 2),
-                               w_in.t().unsqueeze(0).expand(batch, C, inner))
+        x = self.norm(hidden_states)                                            # :430
+        tokens = F.linear(x.view(n, height * width, C), self.proj_in.weight.view(inner, C), self.proj_in.bias)
         for block in self.transformer_blocks:                                   # :487-497
             tokens = block(tokens, encoder_hidden_states=encoder_hidden_states, height=height, width=width)
-        w_out = self.proj_out.weight.view(C, inner)
-        # residual + W_out @ tokens^T  ==  permute(0,3,1,2) then proj_out then + residual   :502-508
-        out = torch.baddbmm(residual.view(batch, C, hw), w_out.unsqueeze(0).expand(batch, C, inner),
-                            tokens.transpose(1, 2))
-        out.add_(self.proj_out.bias.view(1, C, 1))
-        return (out.view(batch, C, height, width),)
+        out = F.linear(tokens, self.proj_out.weight.view(C, inner), self.proj_out.bias)   # :503
+        out = out.view(n, height, width, C).add_(hidden_states)                 # :508
+        return (out,)
 
 
 class TransformerTemporalModel(nn.Module):
-    """transformer_temporal_model_forward, pnp_utils.py:170-220."""
+    """transformer_temporal_model_forward, pnp_utils.py:170-220, on frame-major channels-last rows."""
 
     def __init__(self, num_attention_heads, attention_head_dim, in_channels, cross_attention_dim, norm_num_groups=32):
         super().__init__()
@@ -287,21 +323,25 @@ class TransformerTemporalModel(nn.Module):
             [BasicTransformerBlock(inner, num_attention_heads, attention_head_dim, cross_attention_dim,
                                    double_self_attention=True)])
         self.proj_out = nn.Linear(inner, in_channels)
+        self.ctx: Optional[_Ctx] = None
 
     def forward(self, hidden_states, encoder_hidden_states=None, num_frames: int = 1, **kwargs):
-        bt, C, height, width = hidden_states.shape
-        b = bt // num_frames
-        residual = hidden_states
-        x = self.norm(hidden_states, frames_per_stat=num_frames)               # 5-D GroupNorm, :185-188
-        # [(b t), c, h, w] -> [(b h w), t, c]                                    :189
-        x = x.view(b, num_frames, C, height * width).permute(0, 3, 1, 2).reshape(b * height * width, num_frames, C)
-        x = self.proj_in(x)                                                     # :191
+        par = self.ctx.parallel if self.ctx is not None else None
+        if par is not None and par.world > 1:
+            return (par.temporal_transformer(self, hidden_states, num_frames),)
+        return (self.forward_local(hidden_states, num_frames, None),)
+
+    def forward_local(self, hidden_states, num_frames, gather):
+        """hidden_states [(b t), h, w, C] holding ALL frames of its pixels (h*w may be a pixel shard)."""
+        bt, height, width, C = hidden_states.shape
+        b, S = bt // num_frames, height * width
+        x = self.norm(hidden_states, frames_per_stat=num_frames, gather=gather)  # 5-D GroupNorm, :185-188
+        x = self.proj_in(x.view(bt, S, C))                                      # :191 (the permute at :189 is implicit)
+        shape = TemporalShape(b, num_frames, S)
         for block in self.transformer_blocks:                                   # :194-203
-            x = block(x, encoder_hidden_states=None, height=height, width=width)
+            x = block(x, encoder_hidden_states=None, height=height, width=width, temporal=shape)
         x = self.proj_out(x)                                                    # :206
-        x = (x.view(b, height * width, num_frames, C).permute(0, 2, 3, 1)       # :207-213
-             .reshape(bt, C, height, width))
-        return (x.add_(residual),)                                              # :215
+        return x.view(bt, height, width, C).add_(hidden_states)                 # :207-215
 
 
 # ------------------------------------------------------------------ conv blocks
@@ -321,26 +361,37 @@ class ResnetBlock2D(nn.Module):
         self.output_scale_factor = 1.0
         self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
         self.feature_hook = None  # set by register_resnet_injection
+        self.ctx: Optional[_Ctx] = None
+        self._bias2 = None
 
     def forward(self, input_tensor, temb, scale: float = 1.0):
+        n, H, W, cin = input_tensor.shape
         h = self.norm1(input_tensor, silu=True)                                 # :909-910
-        h = self.conv1(h)                                                       # :939
+        h = conv_nhwc(h, self.conv1)                                            # :939
         t = self.time_emb_proj(F.silu(temb))                                    # :941-948
-        h.add_(t[:, :, None, None])                                             # :952
-        h = self.norm2(h, silu=True, out=h)                                     # :953, :965
-        h = self.conv2(h)                                                       # :968
+        h = self.norm2(h, silu=True, add=t, out=h)                              # `+ temb` :952 fused into norm2 :953, :965
+        if self.conv_shortcut is None:
+            h = conv_nhwc(h, self.conv2)                                        # :968
+            if self.feature_hook is not None:
+                self.feature_hook(self, h)                                      # :970-1004
+            return h.add_(input_tensor)                                         # :1018 (scale factor 1)
+        # 1x1 shortcut conv (:1011-1016) == row GEMM accumulated into conv2's output; its bias rides on
+        # conv2's (a per-channel constant commutes with the per-pixel select of the injection)
+        if self._bias2 is None or self._bias2.device != h.device or self._bias2.dtype != h.dtype:
+            self._bias2 = (self.conv2.bias + self.conv_shortcut.bias).detach()
+        h = conv_nhwc(h, self.conv2, bias=self._bias2)
         if self.feature_hook is not None:
-            self.feature_hook(self, h)                                          # :970-1004
-        if self.conv_shortcut is not None:
-            input_tensor = self.conv_shortcut(input_tensor)                     # :1011-1016
-        return h.add_(input_tensor)                                             # :1018 (scale factor 1)
+            self.feature_hook(self, h)
+        cout = h.shape[-1]
+        h.view(-1, cout).addmm_(input_tensor.view(-1, cin), self.conv_shortcut.weight.view(cout, cin).t())
+        return h
 
 
 class _TemporalTap(nn.Sequential):
     """[GroupNorm, SiLU, (Dropout), Conv3d(k=(3,1,1))] — an nn.Sequential so the state-dict names equal
     diffusers' ("conv1.0.weight", "conv1.2.weight", "conv2.3.weight", ...); executed as GroupNorm(5-D
-    statistics)+SiLU in one kernel and the 3-tap temporal conv as three accumulating batched GEMMs on
-    frame-shifted views (no [B,C,T,H,W] permute and no im2col copy)."""
+    statistics)+SiLU in one kernel and the 3-tap temporal conv as accumulating row GEMMs on frame-shifted
+    row ranges (no [B,C,T,H,W] permute and no im2col copy)."""
 
     def __init__(self, dim_in, dim_out, groups, with_dropout):
         mods = [GroupNormAct(groups, dim_in), nn.SiLU()]
@@ -358,25 +409,26 @@ class _TemporalTap(nn.Sequential):
     def conv(self):
         return self[len(self) - 1]
 
-    def forward(self, x, num_frames):
-        """x: [(b t), C, h, w] frame-major -> same layout."""
-        bt, C, h, w = x.shape
-        b, hw = bt // num_frames, h * w
-        y = self.norm(x, silu=True, frames_per_stat=num_frames)
+    def forward(self, x, num_frames, gather=None):
+        """x: [(b t), h, w, C] frame-major channels-last -> same layout."""
+        bt, h, w, C = x.shape
+        b, S = bt // num_frames, h * w
+        y = self.norm(x, silu=True, frames_per_stat=num_frames, gather=gather)
         conv = self.conv
         co = conv.out_channels
         if self._taps is None or self._taps.device != x.device or self._taps.dtype != x.dtype:
-            self._taps = conv.weight.view(co, C, 3).permute(2, 0, 1).contiguous()  # [tap, co, ci]
+            # [co, ci, 3, 1, 1] -> [tap, ci, co] (right-hand operands of the row GEMMs)
+            self._taps = conv.weight.view(co, C, 3).permute(2, 1, 0).contiguous()
         wp, wc, wn = self._taps[0], self._taps[1], self._taps[2]
-        out = torch.baddbmm(conv.bias.view(1, co, 1), wc.unsqueeze(0).expand(bt, co, C), y.view(bt, C, hw))
+        y2 = y.view(bt * S, C)
+        out = torch.addmm(conv.bias, y2, wc)                                    # centre tap, all frames
+        rows = num_frames * S
         if num_frames > 1:
-            y4, o4 = y.view(b, num_frames, C, hw), out.view(b, num_frames, co, hw)
-            wpe = wp.unsqueeze(0).expand(num_frames - 1, co, C)
-            wne = wn.unsqueeze(0).expand(num_frames - 1, co, C)
             for i in range(b):
-                o4[i, 1:].baddbmm_(wpe, y4[i, :-1])   # tap on frame t-1
-                o4[i, :-1].baddbmm_(wne, y4[i, 1:])   # tap on frame t+1
-        return out.view(bt, co, h, w)
+                r0, r1 = i * rows, (i + 1) * rows
+                out[r0 + S:r1].addmm_(y2[r0:r1 - S], wp)                        # tap on frame t-1
+                out[r0:r1 - S].addmm_(y2[r0 + S:r1], wn)                        # tap on frame t+1
+        return out.view(bt, h, w, co)
 
 
 class TemporalConvLayer(nn.Module):
@@ -392,17 +444,24 @@ class TemporalConvLayer(nn.Module):
         nn.init.zeros_(self.conv4.conv.weight)
         nn.init.zeros_(self.conv4.conv.bias)
         self.feature_hook = None  # set by register_temp_conv_injection
+        self.ctx: Optional[_Ctx] = None
 
     def forward(self, hidden_states, num_frames: int = 1):
-        identity = hidden_states
-        h = self.conv1(hidden_states, num_frames)                               # :1048
-        h = self.conv2(h, num_frames)
-        h = self.conv3(h, num_frames)
-        h = self.conv4(h, num_frames)                                           # :1051
-        h = h.add_(identity)                                                    # :1053
+        par = self.ctx.parallel if self.ctx is not None else None
+        if par is not None and par.world > 1:
+            h = par.temporal_conv(self, hidden_states, num_frames)
+        else:
+            h = self.forward_local(hidden_states, num_frames, None)
         if self.feature_hook is not None:
             self.feature_hook(self, h)                                          # :1059-1082
         return h
+
+    def forward_local(self, hidden_states, num_frames, gather):
+        h = self.conv1(hidden_states, num_frames, gather)                       # :1048
+        h = self.conv2(h, num_frames, gather)
+        h = self.conv3(h, num_frames, gather)
+        h = self.conv4(h, num_frames, gather)                                   # :1051
+        return h.add_(hidden_states)                                            # :1053
 
 
 class Downsample2D(nn.Module):
@@ -411,7 +470,7 @@ class Downsample2D(nn.Module):
         self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=1)
 
     def forward(self, x, scale: float = 1.0):
-        return self.conv(x)
+        return conv_nhwc(x, self.conv)
 
 
 class Upsample2D(nn.Module):
@@ -420,11 +479,13 @@ class Upsample2D(nn.Module):
         self.conv = nn.Conv2d(channels, channels, 3, padding=1)
 
     def forward(self, x, output_size=None, scale: float = 1.0):
+        xc = x.permute(0, 3, 1, 2)                                              # channels_last view
         if output_size is None:
-            x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+            xc = F.interpolate(xc, scale_factor=2.0, mode="nearest")
         else:
-            x = F.interpolate(x, size=output_size, mode="nearest")
-        return self.conv(x)
+            xc = F.interpolate(xc, size=output_size, mode="nearest")
+        y = F.conv2d(xc, self.conv.weight, self.conv.bias, 1, 1).permute(0, 2, 3, 1)
+        return y if y.is_contiguous() else y.contiguous()
 
 
 class _Block3D(nn.Module):
@@ -531,7 +592,7 @@ class CrossAttnUpBlock3D(_Block3D):
                                                       self.temp_attentions):
             res = res_hidden_states_tuple[-1]
             res_hidden_states_tuple = res_hidden_states_tuple[:-1]
-            hidden_states = torch.cat([hidden_states, res], dim=1)
+            hidden_states = torch.cat([hidden_states, res], dim=-1)
             hidden_states = resnet(hidden_states, temb)
             hidden_states = temp_conv(hidden_states, num_frames=num_frames)
             hidden_states = attn(hidden_states, encoder_hidden_states=encoder_hidden_states)[0]
@@ -552,7 +613,7 @@ class UpBlock3D(_Block3D):
         for resnet, temp_conv in zip(self.resnets, self.temp_convs):
             res = res_hidden_states_tuple[-1]
             res_hidden_states_tuple = res_hidden_states_tuple[:-1]
-            hidden_states = torch.cat([hidden_states, res], dim=1)
+            hidden_states = torch.cat([hidden_states, res], dim=-1)
             hidden_states = resnet(hidden_states, temb)
             hidden_states = temp_conv(hidden_states, num_frames=num_frames)
         if self.upsamplers is not None:
@@ -656,6 +717,10 @@ class I2VGenXLUNet(nn.Module):
         self.conv_act = nn.SiLU()
         self.conv_out = nn.Conv2d(boc[0], cfg.out_channels, 3, padding=1)
         self.conv_out.feature_hook = None  # set by register_out_conv_injection
+        self.ctx = _Ctx()
+        for m in self.modules():
+            if isinstance(m, (TransformerTemporalModel, TemporalConvLayer, Attention, ResnetBlock2D)):
+                m.ctx = self.ctx
 
     @property
     def dtype(self):
@@ -684,21 +749,26 @@ class I2VGenXLUNet(nn.Module):
         image_emb = image_emb.view(-1, self.config.in_channels, self.config.cross_attention_dim)
         return torch.cat([encoder_hidden_states, il, image_emb], dim=1)
 
-    def stem(self, sample, image_latents_first):
-        """image-latent conditioning + conv_in + transformer_in (pipeline_i2vgen_xl.py:264-290)."""
-        b, c, T, h, w = sample.shape
+    def stem_condition(self, image_latents_first):
+        """Image-latent conditioning channels [(b t), c, h, w] (pipeline_i2vgen_xl.py:264-279); independent
+        of the timestep, so the step loop computes it once."""
+        b, c, T, h, w = image_latents_first.shape
         il = image_latents_first.permute(0, 2, 1, 3, 4).reshape(b * T, c, h, w)
         il = self.image_latents_proj_in(il)
         il = il.view(b, T, c, h, w).permute(0, 3, 4, 1, 2).reshape(b * h * w, T, c)
         il = self.image_latents_temporal_encoder(il)
-        il = il.reshape(b, h, w, T, c).permute(0, 4, 3, 1, 2)
-        x = torch.cat([sample, il], dim=1)
-        x = x.permute(0, 2, 1, 3, 4).reshape(b * T, 2 * c, h, w)
-        x = self.conv_in(x)
-        return self.transformer_in(x, num_frames=T)[0]
+        return il.reshape(b, h, w, T, c).permute(0, 3, 4, 1, 2).reshape(b * T, c, h, w).contiguous()
+
+    def stem(self, sample_frames, il_frames, num_frames):
+        """cat + conv_in + transformer_in (pipeline_i2vgen_xl.py:282-290).  sample_frames, il_frames:
+        [(b t), c, h, w] (the frames this rank owns); returns channels-last [(b t), h, w, C0]."""
+        x = torch.cat([sample_frames, il_frames], dim=1).permute(0, 2, 3, 1).contiguous()
+        x = conv_nhwc(x, self.conv_in)
+        return self.transformer_in(x, num_frames=num_frames)[0]
 
     def body(self, sample, emb, context_emb, num_frames, forward_upsample_size):
-        """down / mid / up / out, pipeline_i2vgen_xl.py:292-357."""
+        """down / mid / up / out, pipeline_i2vgen_xl.py:292-357, on channels-last [(b t), h, w, C].
+        Returns the noise prediction as [(b t), 4, h, w] (contiguous NCHW)."""
         upsample_size = None
         res_samples = (sample,)
         for blk in self.down_blocks:
@@ -713,22 +783,23 @@ class I2VGenXLUNet(nn.Module):
             res = res_samples[-n:]
             res_samples = res_samples[:-n]
             if i != len(self.up_blocks) - 1 and forward_upsample_size:
-                upsample_size = res_samples[-1].shape[2:]
+                upsample_size = res_samples[-1].shape[1:3]
             if blk.has_cross_attention:
                 sample = blk(sample, res, temb=emb, encoder_hidden_states=context_emb, upsample_size=upsample_size,
                              num_frames=num_frames)
             else:
                 sample = blk(sample, res, temb=emb, upsample_size=upsample_size, num_frames=num_frames)
         sample = self.conv_norm_out(sample, silu=True, out=sample)              # :351-352
-        sample = self.conv_out(sample)                                          # :354
+        sample = conv_nhwc(sample, self.conv_out).permute(0, 3, 1, 2).contiguous()   # :354 -> [(b t), 4, h, w]
         if self.conv_out.feature_hook is not None:
             self.conv_out.feature_hook(self.conv_out, sample)                   # pnp_utils.py:1114-1146
-        return sample.view(-1, num_frames, *sample.shape[1:]).permute(0, 2, 1, 3, 4)
+        return sample
 
     def forward(self, sample, timestep, fps, image_latents, image_embeddings=None, encoder_hidden_states=None,
                 image_latents_first=None, return_dict: bool = False, **kwargs):
         """Stock signature (diffusers I2VGenXLUNet.forward) plus MVOC's `image_latents_first`
-        (I2VGenXLUnetExtension.forward, pipeline_i2vgen_xl.py:109-122).  Returns a 1-tuple."""
+        (I2VGenXLUnetExtension.forward, pipeline_i2vgen_xl.py:109-122).  Single-GPU convenience entry; the
+        step loops use the pieces directly (mvoc_b200/pipeline.py).  Returns a 1-tuple [b, 4, T, h, w]."""
         if not sample.is_cuda:
             raise RuntimeError("mvoc_b200.I2VGenXLUNet runs on CUDA tensors only (no CPU fallback)")
         if image_latents_first is None:
@@ -738,8 +809,10 @@ class I2VGenXLUNet(nn.Module):
         emb = self._embeddings(sample, timestep, fps).repeat_interleave(T, dim=0)
         ctx = self.context(encoder_hidden_states, image_latents, image_embeddings)
         ctx = ctx.repeat_interleave(T, dim=0)
-        x = self.stem(sample, image_latents_first)
-        return (self.body(x, emb, ctx, T, fwd_up),)
+        frames = sample.permute(0, 2, 1, 3, 4).reshape(b * T, c, h, w)
+        x = self.stem(frames, self.stem_condition(image_latents_first), T)
+        out = self.body(x, emb, ctx, T, fwd_up)
+        return (out.view(b, T, *out.shape[1:]).permute(0, 2, 1, 3, 4),)
 
 
 def build_unet(kind: str = "full", seed: int = 0, device="cuda", dtype=torch.bfloat16) -> I2VGenXLUNet:
@@ -747,4 +820,13 @@ def build_unet(kind: str = "full", seed: int = 0, device="cuda", dtype=torch.bfl
     CPU in fp32, then cast/moved.  (Parity tests do not rely on RNG order: they load the oracle's state dict.)"""
     torch.manual_seed(seed)
     m = I2VGenXLUNet(UNetConfig.named(kind)).eval().requires_grad_(False)
-    return m.to(device=device, dtype=dtype)
+    return prepare(m.to(device=device, dtype=dtype))
+
+
+def prepare(unet: I2VGenXLUNet) -> I2VGenXLUNet:
+    """Put the conv weights in channels_last memory format once (cuDNN then runs its NHWC kernels with no
+    per-call filter transform)."""
+    for m in unet.modules():
+        if isinstance(m, nn.Conv2d) and m.kernel_size != (1, 1):
+            m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
+    return unet

@@ -289,3 +289,119 @@ def test_cfg_ddim_step_vs_oracle(cuda_device):
     torch.cuda.synchronize()
     ref3 = ops_ref.ddim_step_ref(u.float(), x, a_prev, a_t)
     assert rel_l2(x3, ref3) <= 1e-5
+
+
+# ------------------------------------------------------------------ channels-last kernels
+GN_NHWC_CASES = [
+    # N, C, H, W, frames_per_stat, silu, eps, with_add
+    (16, 320, 32, 32, 1, True, 1e-5, False),
+    (16, 320, 32, 32, 1, True, 1e-5, True),      # resnet norm2: GN(h + temb)
+    (16, 320, 32, 32, 8, False, 1e-6, False),    # temporal transformer norm (5-D statistics)
+    (8, 960, 64, 64, 1, True, 1e-5, False),
+    (16, 64, 16, 16, 8, True, 1e-5, False),      # reduced UNet: 2 channels per group
+    (4, 1280, 8, 8, 1, True, 1e-5, True),
+    (6, 2560, 16, 16, 1, True, 1e-5, False),
+    (4, 640, 11, 20, 2, True, 1e-5, False),      # non power-of-two spatial size
+]
+
+
+@pytest.mark.parametrize("N,C,H,W,fps,silu,eps,with_add", GN_NHWC_CASES)
+def test_groupnorm_nhwc_vs_oracle(cuda_device, N, C, H, W, fps, silu, eps, with_add):
+    from mvoc_b200 import ops
+
+    torch.manual_seed(C + H + fps)
+    x = (torch.randn(N, C, H, W) * 2.0 + 0.7).bfloat16()
+    wgt = (1.0 + 0.2 * torch.randn(C)).bfloat16()
+    bias = (0.1 * torch.randn(C)).bfloat16()
+    add = (0.5 * torch.randn(N, C)).bfloat16() if with_add else None
+    xin = x.float() + (add.float()[:, :, None, None] if with_add else 0.0)
+    ref = ops_ref.group_norm_ref(xin, wgt.float(), bias.float(), 32, eps, silu, fps)
+    x_cl = x.permute(0, 2, 3, 1).contiguous().to(cuda_device)
+    out = ops.groupnorm_nhwc(x_cl, wgt.to(cuda_device), bias.to(cuda_device), 32, eps, silu, fps,
+                             add.to(cuda_device) if with_add else None)
+    torch.cuda.synchronize()
+    err = rel_l2(out.permute(0, 3, 1, 2), ref)
+    assert err <= 3e-3, f"rel L2 {err:.3e}"
+    inplace = x_cl.clone()
+    ops.groupnorm_nhwc(inplace, wgt.to(cuda_device), bias.to(cuda_device), 32, eps, silu, fps,
+                       add.to(cuda_device) if with_add else None, out=inplace)
+    torch.cuda.synchronize()
+    assert torch.equal(inplace, out)
+
+
+def test_groupnorm_nhwc_sharded_statistics(cuda_device):
+    """Pixel shards + gathered partial statistics == the un-sharded result (multi-GPU temporal GroupNorm)."""
+    from mvoc_b200 import ops
+
+    torch.manual_seed(1)
+    N, S, C, P = 16, 256, 320, 4
+    x = (torch.randn(N, S, C) * 1.5 + 0.3).bfloat16().to(cuda_device)
+    w = (1.0 + 0.2 * torch.randn(C)).bfloat16().to(cuda_device)
+    b = (0.1 * torch.randn(C)).bfloat16().to(cuda_device)
+    full = ops.groupnorm_nhwc(x, w, b, 32, 1e-5, True, 8)
+    shards = [x[:, i * S // P:(i + 1) * S // P].contiguous() for i in range(P)]
+    from mvoc_b200 import _cabi
+
+    lib = _cabi.load()
+    parts = []
+    chunks, _ = ops._gnh_geometry(S // P, C, 0)
+    for sh in shards:
+        part = torch.empty(N, 32, chunks, 2, device=cuda_device)
+        _cabi.check(lib.mvoc_groupnorm_nhwc_stats(sh.data_ptr(), None, part.data_ptr(), N, S // P, C, 32, 0, None), "stats")
+        parts.append(part)
+    allp = torch.stack(parts)
+    outs = [ops.groupnorm_nhwc(sh, w, b, 32, 1e-5, True, 8, gather=lambda p_: allp) for sh in shards]
+    torch.cuda.synchronize()
+    got = torch.cat(outs, dim=1)
+    assert rel_l2(got, full) <= 2e-3
+
+
+@pytest.mark.parametrize("M,F", [(4096, 1280), (1000, 256), (77, 5120)])
+def test_geglu_vs_torch(cuda_device, M, F):
+    from mvoc_b200 import ops
+
+    torch.manual_seed(M)
+    x = (torch.randn(M, 2 * F) * 1.5).bfloat16()
+    a, g = x.float().chunk(2, dim=-1)
+    ref = a * torch.nn.functional.gelu(g)
+    out = ops.geglu(x.to(cuda_device))
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) <= 3e-3
+
+
+@pytest.mark.parametrize("B,T,S,H", [(5, 16, 256, 5), (3, 8, 100, 2), (2, 32, 64, 10)])
+def test_temporal_attention_frames_vs_oracle(cuda_device, B, T, S, H):
+    """Frame-major rows (b, t, pixel) read in place == the reference's [(b h w), T, C] attention."""
+    from mvoc_b200 import ops
+
+    torch.manual_seed(B * T + S)
+    C = H * 64
+    qkv = torch.randn(B * T * S, 3 * C).bfloat16()
+    q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+
+    def to_ref(x):  # (b t p) c -> (b p) t c
+        return x.float().view(B, T, S, C).permute(0, 2, 1, 3).reshape(B * S, T, C)
+
+    ref = ops_ref.sdpa_ref(to_ref(q), to_ref(k), to_ref(v), H)
+    ref = ref.view(B, S, T, C).permute(0, 2, 1, 3).reshape(B * T * S, C)
+    d = qkv.to(cuda_device)
+    out = ops.temporal_attention_frames(d[:, :C], d[:, C:2 * C], d[:, 2 * C:], H, B, T, S)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) <= 1e-2
+
+
+def test_feature_blend_channels_last_bit_exact(cuda_device):
+    """Hidden-state injection on channels-last rows (the Q/K select kernel with base = background)."""
+    from mvoc_b200 import ops, pnp_utils
+
+    n_obj, T, H, W, C = 2, 8, 32, 32, 64
+    nb = n_obj + 3
+    masks = make_masks(n_obj, T, H, W, seed=41)
+    torch.manual_seed(9)
+    x = torch.randn(nb * T, C, H, W).bfloat16()
+    ref = ops_ref.feature_inject_ref(x.float(), masks)
+    xd = x.permute(0, 2, 3, 1).contiguous().to(cuda_device)
+    md = [(mf.to(cuda_device), mb.to(cuda_device)) for mf, mb in masks]
+    ops.qk_blend_(xd, None, pnp_utils._MASKS.tokens(md, H, W, soft=False), n_obj, True)
+    torch.cuda.synchronize()
+    assert torch.equal(xd.permute(0, 3, 1, 2).float().cpu(), ref)

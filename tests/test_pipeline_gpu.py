@@ -36,7 +36,9 @@ def _product_from(oracle_unet, wl, device):
 
     m = I2VGenXLUNet(UNetConfig.named(wl.unet)).eval().requires_grad_(False)
     m.load_state_dict(oracle_unet.state_dict(), strict=True)
-    return m.to(device=device, dtype=torch.bfloat16)
+    from mvoc_b200.unet3d import prepare
+
+    return prepare(m.to(device=device, dtype=torch.bfloat16))
 
 
 def _cond(inputs, device):
@@ -99,7 +101,7 @@ def test_unet_forward_vs_oracle(cuda_device, wl_name):
     pipe = I2VGenXLPipeline(pu, cuda_device)
     init_pnp(pipe, sched, wl)
     pnp_utils.register_time_all(pipe, t, masks_d)
-    out = pipe._unet_forward(bf(sample), t, _cond(inputs, cuda_device))
+    out = pipe._gather_prediction(pipe._unet_forward(bf(sample), t, _cond(inputs, cuda_device)))
     torch.cuda.synchronize()
     err = rel_l2(out, ref)
     print(f"[{wl_name}] product rel L2 {err:.4e}; torch-bf16 envelope {env_err:.4e}")
@@ -180,7 +182,9 @@ def test_unet_forward_vs_reference_golden(cuda_device, case_name):
     ou = spec.build_tiny4(seed=0)
     pu = I2VGenXLUNet(UNetConfig.tiny4()).eval().requires_grad_(False)
     pu.load_state_dict(ou.state_dict(), strict=True)
-    pu = pu.to(cuda_device, torch.bfloat16)
+    from mvoc_b200.unet3d import prepare
+
+    pu = prepare(pu.to(cuda_device, torch.bfloat16))
     pipe = I2VGenXLPipeline(pu, cuda_device)
     cfg = SimpleNamespace(n_steps=50, pnp_f_t=case["pnp_f_t"], pnp_spatial_attn_t=case["pnp_spatial_attn_t"],
                           pnp_temp_attn_t=case["pnp_temp_attn_t"], inject_background=case["inject_background"])
@@ -188,7 +192,8 @@ def test_unet_forward_vs_reference_golden(cuda_device, case_name):
     inp = spec.make_inputs(case)
     masks = [(mf.to(cuda_device), mb.to(cuda_device)) for mf, mb in inp["masks"]]
     pnp_utils.register_time_all(pipe, case["t"], masks)
-    out = pipe._unet_forward(inp["sample"].to(cuda_device, torch.bfloat16), case["t"], _cond(inp, cuda_device))
+    out = pipe._gather_prediction(pipe._unet_forward(inp["sample"].to(cuda_device, torch.bfloat16), case["t"],
+                                                     _cond(inp, cuda_device)))
     torch.cuda.synchronize()
     ref = gold[case_name]
     err = rel_l2(out, ref)
