@@ -75,7 +75,7 @@ int mvoc_attn_fwd(const void* q, const void* k, const void* v, void* o,
  * (injected temporal attn1) and the stock processor on the temporal attn2,
  * transformer_in (i2vgen-xl/pnp_utils.py:170-220 drives them).
  *
- * q,k,v,o: [P, T, H, D], D == 64 contiguous, T in {8, 16, 24, 32};
+ * q,k,v,o: [P, T, H, D], D == 64 contiguous, 1 <= T <= 32 (16 and 32 are the unmasked fast paths);
  * strides in elements for (problem, token, head).  HBM-bound; bf16 only.
  */
 int mvoc_attn_temporal_fwd(const void* q, const void* k, const void* v, void* o,
@@ -161,6 +161,14 @@ int mvoc_groupnorm_nhwc_finalize(const void* partial, const void* counts, void* 
 int mvoc_groupnorm_nhwc_apply(const void* x, void* y, const void* gamma, const void* beta, const void* add,
                               const void* stat, int64_t N, int64_t S, int C, int G, int frames_per_stat,
                               int silu, int dtype, void* stream);
+
+/*
+ * Row-wise LayerNorm over [M, C] (affine, eps): norm1 / norm2 / norm3 of BasicTransformerBlock
+ * (i2vgen-xl/pnp_utils.py:249-250, :295-296, :322).  One warp per row, one read + one write.  C % 8 == 0,
+ * C <= 2048.  y may alias x.
+ */
+int mvoc_layernorm(const void* x, void* y, const void* gamma, const void* beta, int64_t M, int C,
+                   float eps, int dtype, void* stream);
 
 /*
  * Fused GEGLU gate: y[m, j] = x[m, j] * gelu(x[m, F + j]) (exact erf GELU), x [M, 2F] -> y [M, F].

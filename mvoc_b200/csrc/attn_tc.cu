@@ -5,9 +5,11 @@
 //
 // One CTA = one 128-row query tile of one (batch, head); two CTAs per SM.
 //   warps 0-3  softmax: thread i owns query row i (= TMEM lane i), so row
-//              max / row sum need no shuffles
+//              max / row sum need no shuffles; the score row lives in 128 registers
+//              (setmaxnreg moves registers from the data-movement warpgroup to this one)
 //   warp  4    TMA producer: Q once, then a ring of K / V tiles
 //   warp  5    MMA issuer (one lane): S = Q K^T, O += P V; owns the TMEM allocation
+//   warps 6-7  idle (they complete the second warpgroup for setmaxnreg)
 // TMEM columns (fp32): S [0,128)  P [128,192) (bf16 pairs)  O [192,256).
 // Q, K, V are read straight from the projection output [B, N, H*64] through
 // 4-D tensor maps (128-byte swizzle), so no head transpose is ever materialised.
@@ -22,7 +24,7 @@ constexpr int BM = 128;  // query rows per CTA
 constexpr int BN = 128;  // keys per iteration
 constexpr int HD = 64;   // head dim
 constexpr int TILE_BYTES = BM * HD * 2;  // 16 KB: 128 rows x 128 B
-constexpr int THREADS = 192;
+constexpr int THREADS = 256;  // warps 0-3 softmax (warpgroup 0); 4 TMA, 5 MMA, 6-7 idle (warpgroup 1)
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192;
 constexpr float RESCALE_LOG2_THRESHOLD = 8.0f;
@@ -98,6 +100,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     ptx::tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(sgen + L::tmem_ptr_off);
 
+    // Register re-allocation between the warpgroups: 2 CTAs/SM leave 128 registers per thread at launch;
+    // the data-movement warpgroup keeps 48 and hands the rest to the softmax warpgroup, which needs the
+    // whole 128-column score row in registers (208 each: 128*208 + 128*48 = 256*128).
+    if (warp >= 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;" ::: "memory");
     if (warp == 4) {
         // ===================== TMA producer =====================
         if (lane == 0) {
@@ -173,7 +180,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             __syncwarp();
         }
+    }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");
         // ===================== softmax + epilogue (warps 0-3) =====================
         const int row = threadIdx.x;  // query row inside the tile == TMEM lane
         const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
@@ -185,21 +194,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const bool tail = valid < BN;
             ptx::mbar_wait(b_s_full, (uint32_t)j & 1u, 9);
             ptx::tc_fence_after();
-            // pass 1: row max
-            float mx = -INFINITY;
+            // One TMEM read of the whole score row (128 fp32 columns -> 128 registers); S is free for the
+            // next Q K^T as soon as it sits in registers, long before the exponentials are done.
+            uint32_t r[BN];
 #pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld32(tS + c * 32, r);
-                ptx::tmem_wait_ld();
-                if (tail) {  // keys past Nk (zero-filled by TMA) must not take part
+            for (int c = 0; c < BN / 32; ++c)
+                ptx::tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
+            ptx::tmem_wait_ld();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(b_s_free);
+            if (tail) {  // keys past Nk (zero-filled by TMA) must not take part: exp2(-inf) = 0
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i >= valid) r[i] = 0xff800000u;  // -inf
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+                for (int i = 0; i < BN; ++i)
+                    if (i >= valid) r[i] = 0xff800000u;
             }
+            // row max, four independent chains
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < BN; i += 4) {
+                mx0 = fmaxf(mx0, __uint_as_float(r[i]));
+                mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
+                mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
             bool pv_waited = false;
             if (j == 0) {
                 m_used = mx;
@@ -216,41 +234,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     l_sum *= f;
 #pragma unroll
                     for (int c = 0; c < HD / 32; ++c) {
-                        uint32_t r[32];
-                        ptx::tmem_ld32(tO + c * 32, r);
+                        uint32_t o[32];
+                        ptx::tmem_ld32(tO + c * 32, o);
                         ptx::tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-                        ptx::tmem_st32(tO + c * 32, r);
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                        ptx::tmem_st32(tO + c * 32, o);
                     }
                     ptx::tmem_wait_st();
                 }
             }
-            // pass 2: p = exp2((s - m) * scale*log2e), packed to bf16 pairs
+            // p = exp2((s - m) * scale*log2e), packed to bf16 pairs; four independent row-sum chains
             const float neg_m = -m_used * sl2;
             uint32_t pk[BN / 2];
+            float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
 #pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld32(tS + c * 32, r);
-                ptx::tmem_wait_ld();
-                if (tail) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i >= valid) r[i] = 0xff800000u;  // exp2(-inf) = 0
-                }
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(r[i]), sl2, neg_m));
-                    const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 1]), sl2, neg_m));
-                    l_sum += p0 + p1;
-                    __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-                    pk[c * 16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&pb);
-                }
+            for (int i = 0; i < BN; i += 8) {
+                const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 0]), sl2, neg_m));
+                const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 1]), sl2, neg_m));
+                const float p2 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 2]), sl2, neg_m));
+                const float p3 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 3]), sl2, neg_m));
+                const float p4 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 4]), sl2, neg_m));
+                const float p5 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 5]), sl2, neg_m));
+                const float p6 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 6]), sl2, neg_m));
+                const float p7 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 7]), sl2, neg_m));
+                l0 += p0 + p1;
+                l1 += p2 + p3;
+                l2 += p4 + p5;
+                l3 += p6 + p7;
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(p0, p1), b1 = __floats2bfloat162_rn(p2, p3);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(p4, p5), b3 = __floats2bfloat162_rn(p6, p7);
+                pk[i / 2 + 0] = *reinterpret_cast<uint32_t*>(&b0);
+                pk[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&b1);
+                pk[i / 2 + 2] = *reinterpret_cast<uint32_t*>(&b2);
+                pk[i / 2 + 3] = *reinterpret_cast<uint32_t*>(&b3);
             }
-            // S has been consumed: let the MMA warp overwrite it with the next Q K^T
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(b_s_free);
+            l_sum += (l0 + l1) + (l2 + l3);
             // P buffer is free once the previous P V has completed
             if (j > 0 && !pv_waited) {
                 ptx::mbar_wait(b_pv_done, (uint32_t)(j - 1) & 1u, 11);
@@ -258,12 +277,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             if (kPInTmem) {
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t r[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) r[i] = pk[c * 32 + i];
-                    ptx::tmem_st32(tP + c * 32, r);
-                }
+                for (int c = 0; c < 2; ++c)
+                    ptx::tmem_st32(tP + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[c * 32]));
                 ptx::tmem_wait_st();
                 ptx::tc_fence_before();
             } else {

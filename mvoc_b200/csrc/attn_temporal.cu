@@ -52,18 +52,20 @@ struct TAParams {
     int64_t P;        // problems = P_outer * P_inner
     int64_t P_inner;  // problem index = outer * P_inner + inner
     int H;
+    int T;
     // element strides: (outer problem, inner problem, token, head) per tensor
     int64_t q_so, q_sp, q_st, q_sh, k_so, k_sp, k_st, k_sh, v_so, v_sp, v_st, v_sh, o_so, o_sp, o_st, o_sh;
     float scale_log2;
 };
 
-template <int T>
+// TP = rows held in smem (16 or 32); kExact: T == TP (no masking, fully unrolled loads).
+template <int TP, bool kExact>
 __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal_kernel(TAParams p) {
-    constexpr int MT = (T + 15) / 16;   // query m-tiles
-    constexpr int TP = MT * 16;         // padded rows held in smem
-    constexpr int NT = T / 8;           // key n-tiles (exact)
+    constexpr int MT = TP / 16;         // query m-tiles
+    constexpr int NT = TP / 8;          // key n-tiles
     constexpr int KT = MT;              // PV k-steps of 16 keys
     constexpr int TILE = TP * 128;      // bytes per matrix
+    const int T = kExact ? TP : p.T;    // frames actually present
     extern __shared__ __align__(128) uint8_t ta_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t item = (int64_t)blockIdx.x * TA_WARPS + warp;
@@ -76,15 +78,25 @@ __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal_kernel(TAParams p
     const __nv_bfloat16* gq = p.q + po * p.q_so + pi * p.q_sp + (int64_t)h * p.q_sh;
     const __nv_bfloat16* gk = p.k + po * p.k_so + pi * p.k_sp + (int64_t)h * p.k_sh;
     const __nv_bfloat16* gv = p.v + po * p.v_so + pi * p.v_sp + (int64_t)h * p.v_sh;
+    if (kExact) {
 #pragma unroll
-    for (int i = 0; i < (T * 8) / 32; ++i) {
-        const int idx = lane + 32 * i, r = idx >> 3, c = idx & 7;
-        cp_async16(sQ + swz(r, c), gq + (int64_t)r * p.q_st + c * 8);
-        cp_async16(sK + swz(r, c), gk + (int64_t)r * p.k_st + c * 8);
-        cp_async16(sV + swz(r, c), gv + (int64_t)r * p.v_st + c * 8);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    if (TP > T) {  // zero the padding rows (T = 8 or 24)
+        for (int i = 0; i < (TP * 8) / 32; ++i) {
+            const int idx = lane + 32 * i, r = idx >> 3, c = idx & 7;
+            cp_async16(sQ + swz(r, c), gq + (int64_t)r * p.q_st + c * 8);
+            cp_async16(sK + swz(r, c), gk + (int64_t)r * p.k_st + c * 8);
+            cp_async16(sV + swz(r, c), gv + (int64_t)r * p.v_st + c * 8);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    } else {
+        for (int idx = lane; idx < T * 8; idx += 32) {
+            const int r = idx >> 3, c = idx & 7;
+            cp_async16(sQ + swz(r, c), gq + (int64_t)r * p.q_st + c * 8);
+            cp_async16(sK + swz(r, c), gk + (int64_t)r * p.k_st + c * 8);
+            cp_async16(sV + swz(r, c), gv + (int64_t)r * p.v_st + c * 8);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        // zero the padding rows: Q rows give harmless uniform rows that are never stored, K rows are masked
+        // below, V rows must be finite because they meet P = 0
         const Vec16 z = {{0u, 0u, 0u, 0u}};
         for (int idx = lane; idx < (TP - T) * 8; idx += 32) {
             const int r = T + (idx >> 3), c = idx & 7;
@@ -124,6 +136,14 @@ __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal_kernel(TAParams p
                 mma_bf16_16816(s[nt], a[1][0], a[1][1], a[1][2], a[1][3], b2, b3);
             }
         }
+        if (!kExact) {  // keys >= T do not exist
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int key = nt * 8 + 2 * t;
+                if (key >= T) s[nt][0] = s[nt][2] = -INFINITY;
+                if (key + 1 >= T) s[nt][1] = s[nt][3] = -INFINITY;
+            }
+        }
         // ---- softmax over keys (rows g and g+8 of the tile) ---------------
         float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
@@ -156,11 +176,10 @@ __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal_kernel(TAParams p
         for (int dn = 0; dn < 8; ++dn) o[dn][0] = o[dn][1] = o[dn][2] = o[dn][3] = 0.0f;
 #pragma unroll
         for (int kk = 0; kk < KT; ++kk) {
-            const bool hi_valid = (2 * kk + 1) < NT;  // compile-time after unrolling
             const uint32_t a0 = pack_bf16x2(s[2 * kk][0], s[2 * kk][1]);
             const uint32_t a1 = pack_bf16x2(s[2 * kk][2], s[2 * kk][3]);
-            const uint32_t a2 = hi_valid ? pack_bf16x2(s[hi_valid ? 2 * kk + 1 : 0][0], s[hi_valid ? 2 * kk + 1 : 0][1]) : 0u;
-            const uint32_t a3 = hi_valid ? pack_bf16x2(s[hi_valid ? 2 * kk + 1 : 0][2], s[hi_valid ? 2 * kk + 1 : 0][3]) : 0u;
+            const uint32_t a2 = pack_bf16x2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+            const uint32_t a3 = pack_bf16x2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
 #pragma unroll
             for (int dn = 0; dn < 8; dn += 2) {
                 uint32_t b0, b1, b2, b3;
@@ -192,19 +211,12 @@ __global__ void __launch_bounds__(TA_WARPS * 32) attn_temporal_kernel(TAParams p
     }
 }
 
-template <int T>
+template <int TP, bool kExact>
 static int ta_launch(const TAParams& p, cudaStream_t s) {
-    constexpr int TP = ((T + 15) / 16) * 16;
     const size_t smem = (size_t)TA_WARPS * 3 * TP * 128;
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
-        cudaFuncSetAttribute(attn_temporal_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)smem);
-        attr_set = true;
-    }
     const int64_t items = p.P * p.H;
     const int64_t grid = (items + TA_WARPS - 1) / TA_WARPS;
-    attn_temporal_kernel<T><<<(unsigned)grid, TA_WARPS * 32, smem, s>>>(p);
+    attn_temporal_kernel<TP, kExact><<<(unsigned)grid, TA_WARPS * 32, smem, s>>>(p);
     return check_launch("mvoc_attn_temporal_fwd");
 }
 
@@ -242,15 +254,13 @@ static int ta_dispatch(const char* name, const void* q, const void* k, const voi
     p.o_so = st[12]; p.o_sp = st[13]; p.o_st = st[14]; p.o_sh = st[15];
     p.scale_log2 = scale * 1.4426950408889634f;
     cudaStream_t s = (cudaStream_t)stream;
-    switch (T) {
-        case 8: return ta_launch<8>(p, s);
-        case 16: return ta_launch<16>(p, s);
-        case 24: return ta_launch<24>(p, s);
-        case 32: return ta_launch<32>(p, s);
-        default:
-            set_error("%s: T=%d unsupported (8, 16, 24 or 32 frames)", name, T);
-            return MVOC_ERR_UNSUPPORTED;
-    }
+    p.T = T;
+    if (T == 16) return ta_launch<16, true>(p, s);
+    if (T == 32) return ta_launch<32, true>(p, s);
+    if (T >= 1 && T < 16) return ta_launch<16, false>(p, s);
+    if (T > 16 && T < 32) return ta_launch<32, false>(p, s);
+    set_error("%s: T=%d unsupported (1..32 frames)", name, T);
+    return MVOC_ERR_UNSUPPORTED;
 }
 
 extern "C" int mvoc_attn_temporal_fwd(const void* q, const void* k, const void* v, void* o,

@@ -39,9 +39,13 @@ struct GNHParams {
 
 template <typename T>
 __global__ void gnh_stats_kernel(GNHParams p) {
-    extern __shared__ float gnh_smem[];  // s1[C], s2[C], shift[C]
-    const int C = p.C, VC = C >> 3, Cg = C / p.G;
-    float* s1 = gnh_smem;
+    // smem: part1[R][C], part2[R][C] (per-lane partial sums, reduced in a fixed order => deterministic),
+    //       s1[C], s2[C], shift[C]
+    extern __shared__ float gnh_smem[];
+    const int C = p.C, VC = C >> 3, Cg = C / p.G, R = p.R;
+    float* part1 = gnh_smem;
+    float* part2 = part1 + (size_t)R * C;
+    float* s1 = part2 + (size_t)R * C;
     float* s2 = s1 + C;
     float* sh = s2 + C;
     const int n = blockIdx.y, chunk = blockIdx.x;
@@ -53,24 +57,38 @@ __global__ void gnh_stats_kernel(GNHParams p) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) addv[e] = 0.0f;
     if (p.add) unpack8<T>(ld_global16(reinterpret_cast<const T*>(p.add) + (int64_t)n * C + vc * 8), addv);
-    for (int i = threadIdx.x; i < C; i += blockDim.x) s1[i] = s2[i] = 0.0f;
     float shift[8];
-    if (t0 < t1) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) shift[e] = 0.0f;
+    if (t0 < t1) {  // common per-channel shift (first token of the chunk) against cancellation
         unpack8<T>(ld_global16(xb + t0 * C), shift);
 #pragma unroll
         for (int e = 0; e < 8; ++e) shift[e] += addv[e];
     }
-    if (r == 0) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) sh[vc * 8 + e] = shift[e];
-    }
-    __syncthreads();
     float a1[8], a2[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) a1[e] = a2[e] = 0.0f;
-    for (int64_t t = t0 + r; t < t1; t += p.R) {
+    int64_t t = t0 + r;
+    // four independent 16-byte loads in flight per thread
+    for (; t + 3 * R < t1; t += 4 * R) {
+        Vec16 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld_stream16(xb + (t + u * R) * C);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float f[8];
+            unpack8<T>(v[u], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float d = f[e] + addv[e] - shift[e];
+                a1[e] += d;
+                a2[e] += d * d;
+            }
+        }
+    }
+    for (; t < t1; t += R) {
         float f[8];
-        unpack8<T>(ld_global16(xb + t * C), f);
+        unpack8<T>(ld_stream16(xb + t * C), f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const float d = f[e] + addv[e] - shift[e];
@@ -80,8 +98,22 @@ __global__ void gnh_stats_kernel(GNHParams p) {
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        atomicAdd(&s1[vc * 8 + e], a1[e]);
-        atomicAdd(&s2[vc * 8 + e], a2[e]);
+        part1[(size_t)r * C + vc * 8 + e] = a1[e];
+        part2[(size_t)r * C + vc * 8 + e] = a2[e];
+    }
+    if (r == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sh[vc * 8 + e] = shift[e];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float x1 = 0.0f, x2 = 0.0f;
+        for (int rr = 0; rr < R; ++rr) {
+            x1 += part1[(size_t)rr * C + c];
+            x2 += part2[(size_t)rr * C + c];
+        }
+        s1[c] = x1;
+        s2[c] = x2;
     }
     __syncthreads();
     // one thread per group: Chan-merge the per-channel statistics of its C/G channels
@@ -169,13 +201,31 @@ __global__ void gnh_apply_kernel(GNHParams p) {
         sc[e] = ga[e] * ms.y;
         sf[e] = be[e] + (addv[e] - ms.x) * sc[e];
     }
-    for (int64_t t = t0 + r; t < t1; t += p.R) {
+    const int R = p.R;
+    int64_t t = t0 + r;
+    for (; t + 3 * R < t1; t += 4 * R) {  // four independent 16-byte loads in flight per thread
+        Vec16 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld_stream16(xb + (t + u * R) * C);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float f[8];
+            unpack8<T>(v[u], f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float w = f[e] * sc[e] + sf[e];
+                f[e] = p.silu ? silu_f(w) : w;
+            }
+            st_stream16(yb + (t + u * R) * C, pack8<T>(f));
+        }
+    }
+    for (; t < t1; t += R) {
         float f[8];
         unpack8<T>(ld_stream16(xb + t * C), f);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float v = f[e] * sc[e] + sf[e];
-            f[e] = p.silu ? silu_f(v) : v;
+            const float w = f[e] * sc[e] + sf[e];
+            f[e] = p.silu ? silu_f(w) : w;
         }
         st_stream16(yb + t * C, pack8<T>(f));
     }
@@ -264,7 +314,14 @@ extern "C" int mvoc_groupnorm_nhwc_stats(const void* x, const void* add, void* p
     const int threads = (C / 8) * p.R;
     MVOC_REQUIRE(threads >= G, MVOC_ERR_UNSUPPORTED, "mvoc_groupnorm_nhwc_stats: C=%d too small for G=%d", C, G);
     dim3 grid(p.chunks, (unsigned)N);
-    const size_t smem = 3 * (size_t)C * sizeof(float);
+    const size_t smem = (2 * (size_t)p.R + 3) * (size_t)C * sizeof(float);
+    MVOC_REQUIRE(smem <= 96 * 1024, MVOC_ERR_UNSUPPORTED, "mvoc_groupnorm_nhwc_stats: C=%d needs %zu B of smem", C, smem);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(gnh_stats_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        cudaFuncSetAttribute(gnh_stats_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr_set = true;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == MVOC_BF16) gnh_stats_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(p);
     else gnh_stats_kernel<__half><<<grid, threads, smem, st>>>(p);

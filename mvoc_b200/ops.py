@@ -147,7 +147,7 @@ def temporal_attention(
     scale: Optional[float] = None,
     out: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
-    """Attention over frames: q,k,v [P, T, H*64] with T in {8,16,24,32} (warp-per-problem kernel)."""
+    """Attention over frames: q,k,v [P, T, H*64] with T <= 32 (warp-per-problem kernel)."""
     _need_cuda(q, k, v, out)
     P, T, C = q.shape
     if k.shape != q.shape or v.shape != q.shape:
@@ -402,6 +402,23 @@ def geglu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         out = torch.empty(x.shape[:-1] + (F,), dtype=x.dtype, device=x.device)
     with _Timed(("geglu", M, F), 3.0 * M * F * x.element_size()):
         _cabi.check(_cabi.load().mvoc_geglu(x.data_ptr(), out.data_ptr(), M, F, _dt(x), _stream()), "mvoc_geglu")
+    _count()
+    return out
+
+
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Row-wise LayerNorm over the last dim of a contiguous [..., C] tensor (warp per row)."""
+    _need_cuda(x, weight, bias, out)
+    if not x.is_contiguous():
+        raise ValueError("layernorm: x must be contiguous")
+    C = x.shape[-1]
+    M = x.numel() // C
+    if out is None:
+        out = torch.empty_like(x)
+    with _Timed(("layernorm", M, C), 2.0 * x.numel() * x.element_size()):
+        _cabi.check(_cabi.load().mvoc_layernorm(x.data_ptr(), out.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                                                M, C, float(eps), _dt(x), _stream()), "mvoc_layernorm")
     _count()
     return out
 

@@ -33,7 +33,6 @@ import torch.nn.functional as F
 
 from . import ops
 
-TEMPORAL_MAX_TOKENS = 32  # sequences this short go to the warp-per-problem kernel
 
 
 class UNetConfig:
@@ -226,6 +225,13 @@ class Attention(nn.Module):
                                attention_mask=attention_mask)
 
 
+class LayerNormK(nn.LayerNorm):
+    """nn.LayerNorm parameters, executed by mvoc_layernorm (warp per row)."""
+
+    def forward(self, x):
+        return ops.layernorm(x, self.weight, self.bias, self.eps)
+
+
 class GEGLU(nn.Module):
     def __init__(self, dim_in: int, dim_out: int):
         super().__init__()
@@ -264,12 +270,12 @@ class BasicTransformerBlock(nn.Module):
         super().__init__()
         self.only_cross_attention = False
         self.norm_type = "layer_norm"
-        self.norm1 = nn.LayerNorm(dim, eps=1e-5)
+        self.norm1 = LayerNormK(dim, eps=1e-5)
         self.attn1 = Attention(dim, None, num_attention_heads, attention_head_dim, bias=False)
-        self.norm2 = nn.LayerNorm(dim, eps=1e-5)
+        self.norm2 = LayerNormK(dim, eps=1e-5)
         self.attn2 = Attention(dim, None if double_self_attention else cross_attention_dim,
                                num_attention_heads, attention_head_dim, bias=False)
-        self.norm3 = nn.LayerNorm(dim, eps=1e-5)
+        self.norm3 = LayerNormK(dim, eps=1e-5)
         self.ff = FeedForward(dim, activation_fn="geglu")
 
     def forward(self, hidden_states, encoder_hidden_states=None, height=None, width=None,

@@ -105,7 +105,8 @@ def test_attention_rejects_bad_shapes(cuda_device):
         ops.attention(q32, q32, q32, heads=1)  # fp32 unsupported, no fallback
 
 
-@pytest.mark.parametrize("P,T,H", [(1024, 16, 5), (300, 16, 10), (257, 8, 2), (64, 32, 20), (50, 24, 1)])
+@pytest.mark.parametrize("P,T,H", [(1024, 16, 5), (300, 16, 10), (257, 8, 2), (64, 32, 20), (50, 24, 1), (33, 4, 2),
+                                   (17, 2, 1), (9, 19, 3)])
 def test_temporal_attention_vs_oracle(cuda_device, P, T, H):
     from mvoc_b200 import ops
 
@@ -369,7 +370,7 @@ def test_geglu_vs_torch(cuda_device, M, F):
     assert rel_l2(out, ref) <= 3e-3
 
 
-@pytest.mark.parametrize("B,T,S,H", [(5, 16, 256, 5), (3, 8, 100, 2), (2, 32, 64, 10)])
+@pytest.mark.parametrize("B,T,S,H", [(5, 16, 256, 5), (3, 8, 100, 2), (2, 32, 64, 10), (5, 4, 64, 1)])
 def test_temporal_attention_frames_vs_oracle(cuda_device, B, T, S, H):
     """Frame-major rows (b, t, pixel) read in place == the reference's [(b h w), T, C] attention."""
     from mvoc_b200 import ops
@@ -405,3 +406,19 @@ def test_feature_blend_channels_last_bit_exact(cuda_device):
     ops.qk_blend_(xd, None, pnp_utils._MASKS.tokens(md, H, W, soft=False), n_obj, True)
     torch.cuda.synchronize()
     assert torch.equal(xd.permute(0, 3, 1, 2).float().cpu(), ref)
+
+
+@pytest.mark.parametrize("M,C", [(4096, 320), (1000, 640), (333, 1280), (64, 64), (50, 512), (7, 2048)])
+def test_layernorm_vs_torch(cuda_device, M, C):
+    from mvoc_b200 import ops
+
+    torch.manual_seed(M + C)
+    x = (torch.randn(M, C) * 1.7 + 0.4).bfloat16()
+    w = (1.0 + 0.2 * torch.randn(C)).bfloat16()
+    b = (0.1 * torch.randn(C)).bfloat16()
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), w.float(), b.float(), 1e-5)
+    out = ops.layernorm(x.to(cuda_device), w.to(cuda_device), b.to(cuda_device), 1e-5)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) <= 3e-3
+    again = ops.layernorm(x.to(cuda_device), w.to(cuda_device), b.to(cuda_device), 1e-5)
+    assert torch.equal(out, again)
