@@ -40,7 +40,10 @@ struct Smem {
     static constexpr int n_bars = 5 + 4 * kStages;
     static constexpr int tmem_ptr_off = bar_off + n_bars * 8;
     static constexpr int total = tmem_ptr_off + 16;
-    static constexpr int alloc = total + 1024;  // slack to align the base to 1024 B
+    // No alignment slack: the dynamic window is declared __align__(1024) and checked at run time.  Two CTAs
+    // must fit one SM: 2 * (alloc + 1 KB reserved) <= 228 KB — with the 3-stage ring that leaves < 2 KB.
+    static constexpr int alloc = total;
+    static_assert(2 * (alloc + 1024) <= 233472, "two CTAs per SM no longer fit in shared memory");
 };
 
 struct Params {
@@ -55,9 +58,13 @@ __global__ void __launch_bounds__(THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const Params prm) {
     using L = Smem<kPInTmem, kStages>;
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t sbase = smem_u32(smem_raw);
+    uint8_t* sgen = smem_raw;
+    if ((sbase & 1023u) != 0u) {  // 128-byte-swizzled tiles need a 1024-byte aligned base
+        if (threadIdx.x == 0) printf("mvoc attn_fwd_kernel: dynamic smem base 0x%x is not 1024-byte aligned\n", sbase);
+        __trap();
+    }
 
     const uint32_t sQ = sbase + L::q_off;
     const uint32_t sK = sbase + L::k_off;
