@@ -53,7 +53,8 @@ struct Params {
     float scale_log2;
 };
 
-template <bool kPInTmem, int kStages>
+// kEmuMask: bit (k % 8) set => the k-th pair of a score row takes the FMA-pipe exp2 instead of the MUFU.
+template <bool kPInTmem, int kStages, uint32_t kEmuMask>
 __global__ void __launch_bounds__(THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const Params prm) {
@@ -215,14 +216,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 for (int i = 0; i < BN; ++i)
                     if (i >= valid) r[i] = 0xff800000u;
             }
-            // row max, four independent chains
+            // row max: four independent chains of 3-input max (FMNMX3)
             float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < BN; i += 4) {
-                mx0 = fmaxf(mx0, __uint_as_float(r[i]));
-                mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
-                mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
-                mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+            for (int i = 0; i < BN; i += 8) {
+                mx0 = ptx::max3(mx0, __uint_as_float(r[i + 0]), __uint_as_float(r[i + 1]));
+                mx1 = ptx::max3(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                mx2 = ptx::max3(mx2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+                mx3 = ptx::max3(mx3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
             }
             const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
             bool pv_waited = false;
@@ -251,32 +252,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     ptx::tmem_wait_st();
                 }
             }
-            // p = exp2((s - m) * scale*log2e), packed to bf16 pairs; four independent row-sum chains
-            const float neg_m = -m_used * sl2;
+            // p = exp2(s * scale*log2e - m * scale*log2e) on pairs (FFMA2); the exponential goes to the MUFU or,
+            // for the pairs selected by kEmuMask, to the FMA-pipe polynomial; packed row sums (FADD2).
+            const uint64_t sl2_2 = ptx::pack2(sl2, sl2);
+            const uint64_t negm_2 = ptx::pack2(-m_used * sl2, -m_used * sl2);
             uint32_t pk[BN / 2];
-            float l0 = 0.0f, l1 = 0.0f, l2 = 0.0f, l3 = 0.0f;
+            uint64_t la = ptx::pack2(0.0f, 0.0f), lb = la, lc = la, ld = la;
 #pragma unroll
-            for (int i = 0; i < BN; i += 8) {
-                const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 0]), sl2, neg_m));
-                const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 1]), sl2, neg_m));
-                const float p2 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 2]), sl2, neg_m));
-                const float p3 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 3]), sl2, neg_m));
-                const float p4 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 4]), sl2, neg_m));
-                const float p5 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 5]), sl2, neg_m));
-                const float p6 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 6]), sl2, neg_m));
-                const float p7 = ptx::ex2_approx(fmaf(__uint_as_float(r[i + 7]), sl2, neg_m));
-                l0 += p0 + p1;
-                l1 += p2 + p3;
-                l2 += p4 + p5;
-                l3 += p6 + p7;
-                __nv_bfloat162 b0 = __floats2bfloat162_rn(p0, p1), b1 = __floats2bfloat162_rn(p2, p3);
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(p4, p5), b3 = __floats2bfloat162_rn(p6, p7);
-                pk[i / 2 + 0] = *reinterpret_cast<uint32_t*>(&b0);
-                pk[i / 2 + 1] = *reinterpret_cast<uint32_t*>(&b1);
-                pk[i / 2 + 2] = *reinterpret_cast<uint32_t*>(&b2);
-                pk[i / 2 + 3] = *reinterpret_cast<uint32_t*>(&b3);
+            for (int k = 0; k < BN / 2; ++k) {
+                const uint64_t x2 = ptx::fma2(ptx::pack2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1])),
+                                              sl2_2, negm_2);
+                float p0, p1;
+                if ((kEmuMask >> (k & 7)) & 1u) {
+                    ptx::ex2_poly2(x2, p0, p1);
+                } else {
+                    float x0, x1;
+                    ptx::unpack2(x2, x0, x1);
+                    p0 = ptx::ex2_approx(x0);
+                    p1 = ptx::ex2_approx(x1);
+                }
+                const uint64_t p2 = ptx::pack2(p0, p1);
+                if ((k & 3) == 0) la = ptx::add2(la, p2);
+                else if ((k & 3) == 1) lb = ptx::add2(lb, p2);
+                else if ((k & 3) == 2) lc = ptx::add2(lc, p2);
+                else ld = ptx::add2(ld, p2);
+                __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
+                pk[k] = *reinterpret_cast<uint32_t*>(&b);
             }
-            l_sum += (l0 + l1) + (l2 + l3);
+            {
+                float s0, s1;
+                ptx::unpack2(ptx::add2(ptx::add2(la, lb), ptx::add2(lc, ld)), s0, s1);
+                l_sum += s0 + s1;
+            }
             // P buffer is free once the previous P V has completed
             if (j > 0 && !pv_waited) {
                 ptx::mbar_wait(b_pv_done, (uint32_t)(j - 1) & 1u, 11);
@@ -374,20 +381,20 @@ static int make_map(CUtensorMap* m, const void* base, int B, int H, int N, int64
     return MVOC_OK;
 }
 
-template <bool kPInTmem, int kStages>
+template <bool kPInTmem, int kStages, uint32_t kEmuMask>
 static int launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                   const Params& prm, int B, int H, cudaStream_t s) {
     using L = Smem<kPInTmem, kStages>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<kPInTmem, kStages>,
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<kPInTmem, kStages, kEmuMask>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, L::alloc);
         MVOC_REQUIRE(e == cudaSuccess, MVOC_ERR_CUDA, "mvoc_attn_fwd: cudaFuncSetAttribute: %s",
                      cudaGetErrorString(e));
         attr_set = true;
     }
     dim3 grid((prm.Nq + BM - 1) / BM, H, B);
-    attn_fwd_kernel<kPInTmem, kStages><<<grid, THREADS, L::alloc, s>>>(mq, mk, mv, prm);
+    attn_fwd_kernel<kPInTmem, kStages, kEmuMask><<<grid, THREADS, L::alloc, s>>>(mq, mk, mv, prm);
     return check_launch("mvoc_attn_fwd");
 }
 
@@ -410,7 +417,7 @@ extern "C" int mvoc_attn_fwd(const void* q, const void* k, const void* v, void* 
                  "mvoc_attn_fwd: empty problem B=%d H=%d Nq=%d Nk=%d", B, H, Nq, Nk);
     MVOC_REQUIRE(B <= 65535 && H <= 65535, MVOC_ERR_UNSUPPORTED,
                  "mvoc_attn_fwd: B=%d / H=%d exceed the grid limits", B, H);
-    MVOC_REQUIRE(variant >= 0 && variant <= 2, MVOC_ERR_INVALID_ARG,
+    MVOC_REQUIRE(variant >= 0 && variant <= 5, MVOC_ERR_INVALID_ARG,
                  "mvoc_attn_fwd: unknown variant %d", variant);
     const int64_t strides[12] = {q_sb, q_sn, q_sh, k_sb, k_sn, k_sh, v_sb, v_sn, v_sh, o_sb, o_sn, o_sh};
     for (int i = 0; i < 12; ++i)
@@ -434,6 +441,17 @@ extern "C" int mvoc_attn_fwd(const void* q, const void* k, const void* v, void* 
     prm.Nk = Nk;
     prm.scale_log2 = scale * 1.4426950408889634f;
     cudaStream_t s = (cudaStream_t)stream;
-    if (variant == 1) return attn::launch<false, 2>(mq, mk, mv, prm, B, H, s);
-    return attn::launch<true, 3>(mq, mk, mv, prm, B, H, s);
+    // variants (same results up to the exp2 approximation; the tests run all of them):
+    //   1: P through shared memory (SS MMA), all exponentials on the MUFU
+    //   2: P in TMEM (TS MMA), all exponentials on the MUFU
+    //   3 / 4 / 5: P in TMEM, 2 / 3 / 4 of every 8 pairs on the FMA-pipe polynomial
+    //   0: default
+    switch (variant) {
+        case 1: return attn::launch<false, 2, 0x00u>(mq, mk, mv, prm, B, H, s);
+        case 2: return attn::launch<true, 3, 0x00u>(mq, mk, mv, prm, B, H, s);
+        case 3: return attn::launch<true, 3, 0x88u>(mq, mk, mv, prm, B, H, s);
+        case 5: return attn::launch<true, 3, 0xAAu>(mq, mk, mv, prm, B, H, s);
+        case 4:
+        default: return attn::launch<true, 3, 0xA8u>(mq, mk, mv, prm, B, H, s);  // fastest measured on B200
+    }
 }

@@ -184,6 +184,63 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, 
            ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 issue two fp32 ops per slot) ----------------------
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2_round_down(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rm.ftz.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// 2^x for a pair, evaluated on the FMA pipe instead of the MUFU (which is the bottleneck of a D = 64
+// softmax): Cody-Waite split x = floor(x) + f, degree-3 minimax polynomial for 2^f on [0,1) (max rel. error
+// ~9e-5, invisible after the bf16 rounding of P), integer part added to the exponent field.  The technique
+// is the one published with FlashAttention-4; x must be <= 127.
+__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& p0, float& p1) {
+    float x0, x1;
+    unpack2(x2, x0, x1);
+    const uint64_t xc = pack2(fmaxf(x0, -127.0f), fmaxf(x1, -127.0f));
+    const uint64_t magic = pack2(12582912.0f, 12582912.0f);  // 2^23 + 2^22
+    const uint64_t xr = add2_round_down(xc, magic);           // floor(x) in the low mantissa bits
+    const uint64_t xf = sub2(xc, sub2(xr, magic));            // fractional part in [0, 1)
+    uint64_t p = fma2(pack2(0.077119089663028717041015625f, 0.077119089663028717041015625f), xf,
+                      pack2(0.227564394474029541015625f, 0.227564394474029541015625f));
+    p = fma2(p, xf, pack2(0.695146143436431884765625f, 0.695146143436431884765625f));
+    p = fma2(p, xf, pack2(1.0f, 1.0f));
+    float r0, r1, f0, f1;
+    unpack2(xr, r0, r1);
+    unpack2(p, f0, f1);
+    p0 = __int_as_float((__float_as_int(r0) << 23) + __float_as_int(f0));
+    p1 = __int_as_float((__float_as_int(r1) << 23) + __float_as_int(f1));
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -54,7 +54,7 @@ ATTN_CASES = [
 ]
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("B,H,Nq,Nk", ATTN_CASES)
 def test_attention_vs_oracle(cuda_device, B, H, Nq, Nk, variant):
     from mvoc_b200 import ops
@@ -87,7 +87,7 @@ def test_attention_large_logits_and_strided(cuda_device):
     qkv_d = torch.cat([q, k, v], dim=-1).to(cuda_device)
     qd, kd, vd = qkv_d[..., :C], qkv_d[..., C:2 * C], qkv_d[..., 2 * C:]
     ref = ops_ref.sdpa_ref(q.float(), k.float(), v.float(), H)
-    for variant in (1, 2):
+    for variant in (1, 2, 3, 4, 5):
         out = ops.attention(qd, kd, vd, H, variant=variant)
         torch.cuda.synchronize()
         err = rel_l2(out, ref)

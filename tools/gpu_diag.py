@@ -100,7 +100,7 @@ def section_time():
         k = torch.randn(B, Nk, C, device=dev).bfloat16()
         v = torch.randn(B, Nk, C, device=dev).bfloat16()
         fl = 4.0 * B * H * N * Nk * 64
-        for variant in (1, 2):
+        for variant in (1, 2, 3, 4, 5):
             try:
                 t = _time_cuda(lambda: ops.attention(q, k, v, H, variant=variant), iters=5)
                 print(f"  mvoc v{variant} B={B} H={H} N={N} Nk={Nk}: {t:.3f} ms  {fl / t / 1e9:.1f} TF/s")
@@ -135,6 +135,26 @@ def section_time():
         if fps == 1:
             t = _time_cuda(lambda: F.silu(F.group_norm(x, 32, w, b, 1e-5)))
             print(f"  torch GN+SiLU: {t:.4f} ms  {by / t / 1e6:.0f} GB/s")
+    print("== channels-last GroupNorm / LayerNorm / GEGLU (ms, GB/s of algorithmic bytes) ==")
+    for (N, C, H, W, fps) in [(80, 320, 64, 64, 1), (80, 960, 64, 64, 1), (80, 320, 64, 64, 16), (80, 640, 32, 32, 1)]:
+        x = torch.randn(N, H, W, C, device=dev).bfloat16()
+        w = torch.ones(C, device=dev).bfloat16()
+        b = torch.zeros(C, device=dev).bfloat16()
+        by = 2.0 * x.numel() * 2
+        t = _time_cuda(lambda: ops.groupnorm_nhwc(x, w, b, 32, 1e-5, True, fps))
+        print(f"  gn_nhwc N={N} C={C} {H}x{W} fps={fps}: {t:.4f} ms  {by / t / 1e6:.0f} GB/s")
+    for (M, C) in [(327680, 320), (81920, 640), (20480, 1280)]:
+        x = torch.randn(M, C, device=dev).bfloat16()
+        w = torch.ones(C, device=dev).bfloat16()
+        b = torch.zeros(C, device=dev).bfloat16()
+        by = 2.0 * x.numel() * 2
+        t = _time_cuda(lambda: ops.layernorm(x, w, b, 1e-5))
+        t2 = _time_cuda(lambda: F.layer_norm(x, (C,), w, b, 1e-5))
+        print(f"  layernorm M={M} C={C}: {t:.4f} ms  {by / t / 1e6:.0f} GB/s   (torch {t2:.4f} ms)")
+    x = torch.randn(327680, 2560, device=dev).bfloat16()
+    t = _time_cuda(lambda: ops.geglu(x))
+    print(f"  geglu M=327680 F=1280: {t:.4f} ms  {3.0 * 327680 * 1280 * 2 / t / 1e6:.0f} GB/s")
+    del x
     print("== blends ==")
     nb, T, hw, C = 5, 16, 4096, 320
     q = torch.randn(nb * T, hw, C, device=dev).bfloat16()
