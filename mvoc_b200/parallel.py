@@ -42,6 +42,10 @@ class FrameParallel:
             dist.init_process_group(backend=backend)
         return cls(dist.group.WORLD, dist.get_world_size(), dist.get_rank(), device)
 
+    def shutdown(self) -> None:
+        if self.world > 1 and dist.is_initialized():
+            dist.destroy_process_group()
+
     def describe(self) -> str:
         return "single GPU" if self.world == 1 else f"frame-parallel x{self.world} (all-to-all around temporal ops)"
 

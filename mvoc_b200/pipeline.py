@@ -80,12 +80,41 @@ class Conditioning:
 
 
 class I2VGenXLPipeline:
-    def __init__(self, unet, device="cuda", parallel=None):
+    def __init__(self, unet, device="cuda", parallel=None, use_cuda_graphs: bool = False):
         from .parallel import FrameParallel
 
         self.unet = unet
         self.device = torch.device(device)
         self.parallel = parallel or FrameParallel.single(self.device)
+        # A UNet forward is ~2700 launches; enqueuing them from Python takes about as long as the GPU needs
+        # to run them (tools/step_probe.py), and with P GPUs the device work shrinks P-fold while the host
+        # work does not.  With use_cuda_graphs the forward is captured once per hook configuration (which
+        # hooks fire is host-side control flow) and replayed.
+        self.use_cuda_graphs = use_cuda_graphs
+        self._graphs = {}
+        self._graph_pool = None
+        self._t_dev = None
+        self._static_in = {}
+
+    def static_input(self, shape, device) -> torch.Tensor:
+        """Persistent UNet input buffer [n_branches, 4, T, h, w] (captured graphs read from it)."""
+        key = tuple(shape)
+        buf = self._static_in.get(key)
+        if buf is None:
+            buf = torch.empty(key, dtype=self.unet.dtype, device=device)
+            self._static_in[key] = buf
+        return buf
+
+    def step_kinds(self, timesteps, masks) -> list:
+        """Indices of the first step of every distinct hook configuration in `timesteps` (host-side only)."""
+        seen, firsts = set(), []
+        for i, t in enumerate(timesteps):
+            pnp_utils.register_time_all(self, t, masks)
+            sig = pnp_utils.hook_signature(self.unet)
+            if sig not in seen:
+                seen.add(sig)
+                firsts.append(i)
+        return firsts
         self.scheduler: Optional[DDIMSchedule] = None
         self._cond_cache = None
 
@@ -110,11 +139,50 @@ class I2VGenXLPipeline:
             fps_emb = unet.fps_embedding(unet.time_proj(cond.fps).to(unet.dtype))
             cache = {"key": cond, "ctx": ctx, "il": il, "fps_emb": fps_emb}
             self._cond_cache = cache
-        ts = torch.full((b,), int(t), dtype=torch.int64, device=sample.device)
+        if self._t_dev is None:
+            self._t_dev = torch.zeros(1, dtype=torch.int64, device=sample.device)
+        self._t_dev.fill_(int(t))        # device-side timestep: the captured graph reads it at replay time
+        if not self.use_cuda_graphs:
+            return self._unet_body(sample, cond, cache, (f0, f1))
+        static = self.static_input(sample.shape, sample.device)
+        if sample.data_ptr() != static.data_ptr():
+            static.copy_(sample)
+        sample = static
+        key = (pnp_utils.hook_signature(unet), tuple(sample.shape), id(cond), par.world)
+        entry = self._graphs.get(key)
+        if entry is None:
+            # eager warm-up on a side stream (lazy weight fusions, cuDNN autotune, mask caches), then capture
+            side = torch.cuda.Stream(device=sample.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._unet_body(sample, cond, cache, (f0, f1))
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            graph = torch.cuda.CUDAGraph()
+            timer = ops._timer
+            ops.set_timer(None)          # per-launch events cannot be recorded inside a capture
+            try:
+                with torch.cuda.graph(graph, pool=self._graph_pool):
+                    out = self._unet_body(sample, cond, cache, (f0, f1))
+            finally:
+                ops.set_timer(timer)
+            entry = (graph, out)
+            self._graphs[key] = entry
+        entry[0].replay()
+        return entry[1]
+
+    def _unet_body(self, sample, cond, cache, frames):
+        unet = self.unet
+        b, c, T, h, w = sample.shape
+        f0, f1 = frames
+        tl = f1 - f0
+        ts = self._t_dev.expand(b)
         t_emb = unet.time_embedding(unet.time_proj(ts).to(unet.dtype))
         emb = (t_emb + cache["fps_emb"]).repeat_interleave(tl, dim=0)            # :196-197
-        frames = sample[:, :, f0:f1].permute(0, 2, 1, 3, 4).reshape(b * tl, c, h, w)   # :283
-        x = unet.stem(frames, cache["il"], T)                                   # :282-290
+        frm = sample[:, :, f0:f1].permute(0, 2, 1, 3, 4).reshape(b * tl, c, h, w)     # :283
+        x = unet.stem(frm, cache["il"], T)                                      # :282-290
         fwd_up = any(s % (2 ** unet.num_upsamplers) != 0 for s in (h, w))
         out = unet.body(x, emb, cache["ctx"], T, fwd_up)                        # [(b t_local), 4, h, w]
         return out.view(b, tl, *out.shape[1:])
@@ -163,7 +231,7 @@ class I2VGenXLPipeline:
         T = latents.shape[2]
         mask_f = torch.stack([m[0][0, 0].reshape(-1).float() for m in obj_mask]).contiguous()  # [n_obj, T*h*w]
         masks = list(obj_mask)
-        unet_in = torch.empty((nb,) + tuple(latents.shape[1:]), dtype=self.unet.dtype, device=latents.device)
+        unet_in = self.static_input((nb,) + tuple(latents.shape[1:]), latents.device)
         objs = torch.empty((n_obj,) + tuple(latents.shape[1:]), dtype=torch.float32, device=latents.device)
         bg = torch.empty(tuple(latents.shape[1:]), dtype=torch.float32, device=latents.device)
         host_out = torch.empty(latents.shape, dtype=latents.dtype).pin_memory() if host_io else None

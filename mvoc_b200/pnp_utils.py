@@ -269,6 +269,20 @@ def register_time_all(model, t, mask):
         setattr(m, "mask", mask)
 
 
+def hook_signature(unet) -> tuple:
+    """Which hooks fire at the `t` last pushed by register_time_all — the control-flow key of one UNet
+    forward (CUDA-graph capture in mvoc_b200.pipeline is keyed on it)."""
+    sig = []
+    blk = unet.up_blocks[-1]
+    for m in list(blk.resnets) + list(blk.temp_convs) + [unet.conv_out]:
+        sig.append(getattr(m, "feature_hook", None) is not None and hasattr(m, "t") and _fires(m))
+    for bi, li in injected_attention_sites(unet):
+        for grp in ("attentions", "temp_attentions"):
+            p = getattr(unet.up_blocks[bi], grp)[li].transformer_blocks[0].attn1.processor
+            sig.append(isinstance(p, _InjectingProcessor) and hasattr(p, "t") and _fires(p))
+    return tuple(sig)
+
+
 def register_time(model, t):
     """Older helper kept for API parity (pnp_utils.py:36-45)."""
     for bi, li in injected_attention_sites(model.unet):

@@ -50,10 +50,10 @@ def _cond(inputs, device):
                         inputs["fps"].to(device))
 
 
-def _run_product_composite(wl, sched, inputs, unet, device, max_steps, host_io=False):
+def _run_product_composite(wl, sched, inputs, unet, device, max_steps, host_io=False, graphs=False):
     from mvoc_b200.pipeline import I2VGenXLPipeline, LatentBank, init_pnp
 
-    pipe = I2VGenXLPipeline(unet, device)
+    pipe = I2VGenXLPipeline(unet, device, use_cuda_graphs=graphs)
     init_pnp(pipe, sched, wl)
     banks = [LatentBank(src, device, pin_host=host_io) for src in inputs["source_latents"]]
     masks = [(mf.to(device), mb.to(device)) for mf, mb in inputs["masks"]]
@@ -136,6 +136,12 @@ def test_composite_multi_step_reduced2(cuda_device):
     assert err <= 5e-2
     out_h = _run_product_composite(wl, sched, inputs, _product_from(ou, wl, cuda_device), cuda_device, 4, host_io=True)
     assert torch.equal(out.cpu(), out_h.cpu())
+    # CUDA-graph replay of the UNet forward (one graph per hook configuration) == eager launches.
+    # 7 steps: step 0 fuses, steps 0-4 inject features, steps 5-6 only inject attention => 2 graphs, replayed
+    wl7 = wl
+    eager7 = _run_product_composite(wl7, sched, inputs, _product_from(ou, wl, cuda_device), cuda_device, 7)
+    graph7 = _run_product_composite(wl7, sched, inputs, _product_from(ou, wl, cuda_device), cuda_device, 7, graphs=True)
+    assert torch.equal(eager7.cpu(), graph7.cpu())
 
 
 def test_invert_reduced(cuda_device, tmp_path):

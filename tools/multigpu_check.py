@@ -34,8 +34,8 @@ def main():
     unet = build_unet(wl.unet, seed=0, device=dev)
     bf = lambda x: x.to(device=dev, dtype=torch.bfloat16)
 
-    def run(parallel):
-        pipe = I2VGenXLPipeline(unet, dev, parallel=parallel)
+    def run(parallel, graphs=False):
+        pipe = I2VGenXLPipeline(unet, dev, parallel=parallel, use_cuda_graphs=graphs)
         init_pnp(pipe, sched, wl)
         cond = Conditioning(bf(inputs["prompt_embeds"]), bf(inputs["image_embeddings"]),
                             bf(inputs["image_latents_first"]), bf(inputs["image_latents"]), inputs["fps"].to(dev))
@@ -50,12 +50,18 @@ def main():
 
     sharded = run(par)
     par.barrier()
+    sharded_graph = run(par, graphs=True)     # NCCL all-to-alls captured inside the CUDA graphs
+    par.barrier()
     if par.rank == 0:
         single = run(FrameParallel.single(dev))
         err = float((sharded - single).norm() / single.norm())
-        print(f"[multigpu_check] {wl_name} x{par.world} ranks, {steps} steps: rel L2 vs single GPU = {err:.3e}")
+        same = bool(torch.equal(sharded, sharded_graph))
+        print(f"[multigpu_check] {wl_name} x{par.world} ranks, {steps} steps: rel L2 vs single GPU = {err:.3e}; "
+              f"graph replay == eager: {same}")
         assert err <= 1e-2, err
+        assert same
     par.barrier()
+    par.shutdown()
 
 
 if __name__ == "__main__":
