@@ -95,6 +95,8 @@ class I2VGenXLPipeline:
         self._graph_pool = None
         self._t_dev = None
         self._static_in = {}
+        self.scheduler: Optional[DDIMSchedule] = None
+        self._cond_cache = None
 
     def static_input(self, shape, device) -> torch.Tensor:
         """Persistent UNet input buffer [n_branches, 4, T, h, w] (captured graphs read from it)."""
