@@ -303,7 +303,7 @@ def run_mvoc(args):
     ms_eager_total = k0.elapsed_time(k1)
 
     if rank != 0:
-        par.shutdown()
+        _finish(pipe, par)
         return
     peaks = measured_peaks()
     frames_per_s = wl.n_frames / (wl.n_steps * ms_step / 1e3)
@@ -378,7 +378,21 @@ def run_mvoc(args):
     }
     print(json.dumps(line))
     sys.stdout.flush()
-    par.shutdown()
+    _finish(pipe, par)
+
+
+def _finish(pipe, par):
+    """Leave without running destructors when ranks > 1: captured CUDA graphs hold NCCL kernels, and tearing
+    the communicator / graphs down at interpreter exit can block forever.  Results are already printed."""
+    import torch
+
+    pipe._graphs.clear()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if par.world > 1:
+        par.barrier()
+        os._exit(0)
 
 
 def main():
