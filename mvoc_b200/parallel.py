@@ -87,20 +87,20 @@ class FrameParallel:
         sp = S // P
         if S % P != 0:
             raise ValueError(f"h*w={S} is not divisible by world_size={P}")
-        send = x.view(b, tl, P, sp, C).permute(2, 0, 1, 3, 4).contiguous()       # [dst, b, tl, sp, C]
+        send = x.contiguous().view(b, tl, P, sp, C).permute(2, 0, 1, 3, 4).contiguous()   # [dst, b, tl, sp, C]
         recv = torch.empty_like(send)                                            # [src, b, tl, sp, C]
         dist.all_to_all_single(recv, send, group=self.group)
-        return recv.permute(1, 0, 2, 3, 4).reshape(b * num_frames, 1, sp, C)     # frame = src*tl + i
+        return recv.permute(1, 0, 2, 3, 4).contiguous().view(b * num_frames, 1, sp, C)   # frame = src*tl + i
 
     def to_frame_shards(self, y: torch.Tensor, num_frames: int, h: int, w: int) -> torch.Tensor:
         """Inverse of to_pixel_shards: [(b T), 1, S/P, C] -> [(b t_local), h, w, C]."""
         P = self.world
         bT, _, sp, C = y.shape
         b, tl = bT // num_frames, num_frames // P
-        send = y.view(b, P, tl, sp, C).permute(1, 0, 2, 3, 4).contiguous()       # [dst(frame owner), b, tl, sp, C]
+        send = y.contiguous().view(b, P, tl, sp, C).permute(1, 0, 2, 3, 4).contiguous()   # [dst(frame owner), b, tl, sp, C]
         recv = torch.empty_like(send)                                            # [src(pixel owner), b, tl, sp, C]
         dist.all_to_all_single(recv, send, group=self.group)
-        return recv.permute(1, 2, 0, 3, 4).reshape(b * tl, h, w, C)              # pixel = src*sp + j
+        return recv.permute(1, 2, 0, 3, 4).contiguous().view(b * tl, h, w, C)    # pixel = src*sp + j
 
     def gather_partials(self, partial: torch.Tensor) -> torch.Tensor:
         """GroupNorm partial statistics of every rank's pixel shard: [N,G,chunks,2] -> [P,N,G,chunks,2]."""
@@ -117,7 +117,7 @@ class FrameParallel:
         dist.all_gather_into_tensor(out, x, group=self.group)
         out = out.view((self.world,) + tuple(x.shape))
         k, tl = x.shape[0], x.shape[1]
-        return out.permute(1, 0, 2, *range(3, out.dim())).reshape(k, self.world * tl, *x.shape[2:])
+        return out.permute(1, 0, 2, *range(3, out.dim())).contiguous().view(k, self.world * tl, *x.shape[2:])
 
     # ------------------------------------------------------------------ temporal operators on pixel shards
     def temporal_transformer(self, module, hidden_states: torch.Tensor, num_frames: int) -> torch.Tensor:

@@ -49,7 +49,13 @@ def _full_tensor(b, T, h, w, C):
 
 
 def check_relayout_roundtrip(par):
-    b, T, h, w, C = 3, 8, 4, 6, 5
+    # second shape: h == world and S/world == w, where a permute+reshape can silently stay a strided VIEW
+    # (the 8-GPU run at the 8x8 level hit exactly that) — outputs must be contiguous
+    for (b, T, h, w, C) in [(3, 8, 4, 6, 5), (2, 2 * par.world, par.world, 3, 4)]:
+        _relayout_case(par, b, T, h, w, C)
+
+
+def _relayout_case(par, b, T, h, w, C):
     full = _full_tensor(b, T, h, w, C)
     f0, f1 = par.frame_range(T)
     local = full[:, f0:f1].reshape(b * (f1 - f0), h, w, C).contiguous()
@@ -59,6 +65,7 @@ def check_relayout_roundtrip(par):
     assert torch.equal(px, expect), "pixel shard does not hold (all frames) x (own pixels) in (b, t, p) order"
     back = par.to_frame_shards(px, T, h, w)
     assert torch.equal(back, local)
+    assert px.is_contiguous() and back.is_contiguous()
 
 
 def check_gathers(par):
