@@ -261,10 +261,12 @@ def run_mvoc(args):
     if rank == 0:
         clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.nvtx.range_push("mvoc_timed_region")   # `ncu --nvtx --nvtx-include "mvoc_timed_region/"`
     ev0.record()
     final = loop(0, K)
     ev1.record()
     barrier()
+    torch.cuda.nvtx.range_pop()
     clk = clocks.stop() if rank == 0 else None
     ms_total = par.max_over_ranks(ev0.elapsed_time(ev1))
     ms_step = ms_total / K
