@@ -150,6 +150,28 @@ def main():
         print(case["name"], tuple(y.shape), float(y.std()))
     torch.save(out, os.path.join(HERE, "unet_extension_forward_tiny4.pt"))
 
+    # mask_preprocess (utils.py:92-154) on small synthetic PNG masks committed under tests/golden/masks
+    from PIL import Image, ImageDraw, ImageFilter
+
+    mdir = os.path.join(HERE, "masks")
+    os.makedirs(os.path.join(mdir, "dynamic"), exist_ok=True)
+    for i in range(5):  # 5 files: the reference truncates to `frames` (= 4) after a numeric sort
+        im = Image.new("L", (128, 96), 0)
+        ImageDraw.Draw(im).ellipse([20 + 6 * i, 24, 70 + 6 * i, 70], fill=255)
+        im = im.filter(ImageFilter.GaussianBlur(2.5))
+        if i == 2:
+            im = im.convert("RGB")  # the demo folders mix modes (P / L / RGB)
+        im.save(os.path.join(mdir, "dynamic", ["000.png", "001.png", "002.png", "003.png", "010.png"][i]))
+    im = Image.new("L", (128, 96), 0)
+    ImageDraw.Draw(im).rectangle([30, 10, 90, 60], fill=200)
+    im.filter(ImageFilter.GaussianBlur(1.5)).save(os.path.join(mdir, "static.png"))
+    mg = {}
+    for name, path in (("dynamic", os.path.join(mdir, "dynamic")), ("static", os.path.join(mdir, "static.png"))):
+        mf, mb = ref_utils.mask_preprocess(path, "cpu", torch.float32, 1, 4, 4, downscale=8)   # real reference code
+        mg[name] = (mf.clone(), mb.clone())
+        print("mask", name, tuple(mf.shape), float(mb.float().mean()))
+    torch.save(mg, os.path.join(HERE, "mask_preprocess.pt"))
+
     # wire format: what the reference's loader reads back from a file written like pipeline:1990-1993
     lat = torch.randn(1, 4, 4, 8, 8, generator=torch.Generator().manual_seed(5)).half()
     d = os.path.join(HERE, "ddim_latents_fixture")

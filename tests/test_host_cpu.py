@@ -253,3 +253,155 @@ def test_latent_fusion_keeps_background_outside_masks():
     assert torch.equal(out[outside], bg[outside])              # r = 0: pure background outside every mask
     inside1 = masks[1][0] == 1
     assert torch.allclose(out[inside1], objs[1][inside1])
+
+
+# ------------------------------------------------------------------ masks: host preparation vs reference / oracle
+def test_mask_preprocess_matches_the_reference_function():
+    """mvoc_b200.utils.mask_preprocess == the reference's utils.mask_preprocess (utils.py:92-154) on the PNG
+    fixtures of tests/golden/masks (golden produced by the reference's own function, make_golden.py)."""
+    from mvoc_b200.utils import mask_preprocess
+
+    gdir = os.path.join(ROOT, "tests", "golden")
+    gold = torch.load(os.path.join(gdir, "mask_preprocess.pt"), map_location="cpu")
+    for name, path in (("dynamic", os.path.join(gdir, "masks", "dynamic")),
+                       ("static", os.path.join(gdir, "masks", "static.png"))):
+        mf, mb = mask_preprocess(path, "cpu", torch.float32, 1, 4, 4, downscale=8)
+        rf, rb = gold[name]
+        assert mf.shape == rf.shape == (1, 4, 4, 12, 16) and mb.dtype == torch.bool
+        assert torch.equal(mf, rf) and torch.equal(mb, rb)
+    # the dynamic folder holds 5 numbered files; frame 3 must be "003.png", not "010.png" (numeric sort + cut)
+    assert not torch.equal(gold["dynamic"][0][0, 0, 3], gold["dynamic"][0][0, 0, 2])
+
+
+def _emulate_qk_blend(x, tokens, n_obj, base_slot):
+    """The contract of mvoc_qk_blend in include/mvoc_b200.h, in plain torch (test-side emulation)."""
+    nb = n_obj + 3
+    C = x.shape[-1]
+    v = x.reshape(nb, -1, C).clone()
+    acc = v[base_slot].clone()
+    for j in range(n_obj):
+        m = tokens[j].to(torch.float32)[:, None]
+        if tokens.dtype == torch.uint8:
+            acc = torch.where(m != 0, v[j + 1], acc)
+        else:
+            acc = acc * (1 - m) + v[j + 1] * m
+    v[n_obj + 1] = acc
+    v[n_obj + 2] = acc
+    return v.reshape(x.shape)
+
+
+@pytest.mark.parametrize("n_obj", [1, 2, 3])
+@pytest.mark.parametrize("inject_background", [False, True])
+def test_token_masks_reproduce_the_reference_injection(n_obj, inject_background):
+    """Host-side mask preparation (nearest resize, (frame, pixel) token order, u8 / f32) fed through the
+    kernel CONTRACT gives exactly the reference's spatial / temporal / feature injection."""
+    from mvoc_b200 import pnp_utils
+    from mvoc_b200.synthetic import make_masks
+    from oracle import ops_ref
+
+    T, H, W, h, w, C = 4, 16, 16, 8, 8, 16
+    nb = n_obj + 3
+    masks = make_masks(n_obj, T, H, W, seed=5)
+    cache = pnp_utils._MaskCache()
+    base = 0 if inject_background else n_obj + 2
+    torch.manual_seed(1)
+    # spatial: rows [nb*T, h*w, C]
+    q = torch.randn(nb * T, h * w, C)
+    ref_q, _ = ops_ref.spatial_qk_inject_ref(q, q.clone(), masks, h, w, inject_background)
+    got = _emulate_qk_blend(q, cache.tokens(masks, h, w, soft=False), n_obj, base)
+    assert torch.equal(got, ref_q)
+    # temporal: the reference works on [(b h w), T, C]; the product keeps frame-major rows [(b t), h*w, C]
+    qt = torch.randn(nb * h * w, T, C)
+    ref_t, _ = ops_ref.temporal_qk_inject_ref(qt, qt.clone(), masks, h, w, inject_background)
+    frame_major = qt.view(nb, h * w, T, C).permute(0, 2, 1, 3).reshape(nb * T, h * w, C)
+    got_t = _emulate_qk_blend(frame_major, cache.tokens(masks, h, w, soft=True), n_obj, base)
+    back = got_t.view(nb, T, h * w, C).permute(0, 2, 1, 3).reshape(nb * h * w, T, C)
+    assert torch.allclose(back, ref_t, atol=1e-6)
+    # features: NCHW in the reference, channels-last rows in the product, base = background always
+    x = torch.randn(nb * T, C, H, W)
+    ref_x = ops_ref.feature_inject_ref(x, masks)
+    rows = x.permute(0, 2, 3, 1).reshape(nb * T, H * W, C)
+    got_x = _emulate_qk_blend(rows, cache.tokens(masks, H, W, soft=False), n_obj, 0)
+    assert torch.equal(got_x.view(nb * T, H, W, C).permute(0, 3, 1, 2), ref_x)
+    planes = cache.feature_planes(masks)
+    assert planes.shape == (n_obj, T, H * W) and planes.dtype == torch.uint8
+    assert torch.equal(planes.view(n_obj, -1), cache.tokens(masks, H, W, soft=False))
+
+
+def test_hook_signature_and_step_kinds():
+    """Two hook configurations in the boat_surf schedule: conv + attention injection (steps 0-4), attention
+    only (steps 5-49) => two captured graphs; computed without touching the GPU."""
+    from mvoc_b200 import pnp_utils
+    from mvoc_b200.pipeline import I2VGenXLPipeline, init_pnp
+    from mvoc_b200.scheduler import DDIMSchedule
+    from mvoc_b200.unet3d import I2VGenXLUNet, UNetConfig
+
+    pipe = I2VGenXLPipeline(I2VGenXLUNet(UNetConfig.reduced()), "cpu")
+    sched = DDIMSchedule(50)
+    cfg = SimpleNamespace(n_steps=50, pnp_f_t=0.1, pnp_spatial_attn_t=1.0, pnp_temp_attn_t=1.0, inject_background=False)
+    init_pnp(pipe, sched, cfg)
+    assert pipe.step_kinds(sched.timesteps, []) == [0, 5]
+    pnp_utils.register_time_all(pipe, 981, [])
+    sig0 = pnp_utils.hook_signature(pipe.unet)
+    pnp_utils.register_time_all(pipe, 21, [])
+    sig1 = pnp_utils.hook_signature(pipe.unet)
+    assert sig0 != sig1 and all(sig0) and any(sig1) and not all(sig1)
+    cfg2 = SimpleNamespace(n_steps=50, pnp_f_t=0.2, pnp_spatial_attn_t=0.2, pnp_temp_attn_t=0.5, inject_background=False)
+    init_pnp(pipe, sched, cfg2)
+    assert pipe.step_kinds(sched.timesteps, []) == [0, 10, 25]
+
+
+def test_latent_bank_and_wire_format(tmp_path):
+    from mvoc_b200.pipeline import LatentBank, save_ddim_latents_at_t
+    from mvoc_b200.utils import load_ddim_latents_at_T
+
+    ts = [981, 961, 941]
+    data = {t: torch.full((1, 4, 2, 4, 4), float(t)).half() for t in ts}
+    for t, x in data.items():
+        save_ddim_latents_at_t(x, t, str(tmp_path))
+    assert sorted(os.listdir(tmp_path)) == ["ddim_latents_941.pt", "ddim_latents_961.pt", "ddim_latents_981.pt"]
+    bank = LatentBank.from_dir(str(tmp_path), ts, "cpu")
+    assert bank.data.shape == (3, 4, 2, 4, 4) and bank.data.dtype == torch.float32
+    assert float(bank.at(961).mean()) == 961.0
+    assert float(load_ddim_latents_at_T(str(tmp_path)).float().mean()) == 981.0
+
+
+# ------------------------------------------------------------------ script / config contract
+REF_CFG = "/root/reference/i2vgen-xl/configs"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_CFG), reason="reference configs only exist in the build container")
+def test_reference_config_files_load_unchanged():
+    """The reference's own template.yaml + group_config.json go through the loader and the path joins of
+    composite.py:97-106 / inverse.py:143-150 without edits."""
+    from mvoc_b200 import composite, config as cfgmod
+
+    entries = list(cfgmod.iter_configs(f"{REF_CFG}/group_composite/template.yaml",
+                                       f"{REF_CFG}/group_composite/group_config.json"))
+    assert len(entries) == 7
+    c = composite.resolve_paths(entries[0])
+    assert c.video_name == "boat_surf" and c.image_size == [1280, 720]
+    assert c.obj_mask_path == ["../demo/boat_surf/boat_mask", "../demo/boat_surf/surf_mask"]
+    assert c.bg_ddim_latents_path == "../inversions/i2vgen-xl/boat_surf/ddim_latents"
+    assert c.output_dir == "../Results/MVOC-Demo/i2vgen-xl/boat_surf/sailboat and surfing/"
+    assert composite.latent_geometry(c) == (16, 90, 160)
+    assert (c.pnp_f_t, c.pnp_spatial_attn_t, c.pnp_temp_attn_t, c.fusion_step) == (0.1, 1.0, 1.0, [0, 1])
+    for e in entries:   # every shipped entry has exactly two objects (the reference's hard-coded // 5)
+        assert len(e.obj_mask_path) == 2 and len(e.obj_ddim_latents_path) == 2
+    inv = list(cfgmod.iter_configs(f"{REF_CFG}/group_inversion/template.yaml",
+                                   f"{REF_CFG}/group_inversion/group_config.json"))
+    assert inv and inv[0].inverse_config.n_steps == 500 and inv[0].inverse_config.cfg == 1.0
+    assert inv[0].inverse_config.image_size == [1280, 720]          # ${image_size} keeps the list type
+    assert inv[0].inverse_config.output_dir == "../inversions/i2vgen-xl/boat_surf/ddim_latents"
+    assert inv[0].recon_config.ddim_latents_path == inv[0].inverse_config.output_dir
+
+
+def test_cli_parsers_keep_the_reference_flags():
+    from mvoc_b200 import composite, inverse
+
+    a = composite.build_parser().parse_args(["--template_config", "t.yaml", "--configs_json", "c.json"])
+    assert (a.template_config, a.configs_json) == ("t.yaml", "c.json")
+    d = composite.build_parser().parse_args([])
+    assert d.template_config == "./configs/group_composite/template.yaml"       # composite.py:229-235
+    i = inverse.build_parser().parse_args([])
+    assert i.configs_json == "./configs/group_inversion/group_config.json"      # inverse.py:231-235
