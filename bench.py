@@ -102,6 +102,12 @@ def measured_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
 
 
+def workload_description(wl) -> str:
+    return (f"{wl.name}: full i2vgen-xl UNet random-init, {wl.n_frames} frames x {wl.latent_h}x{wl.latent_w} "
+            f"latents, bg+{wl.n_obj} objects, {wl.n_steps}-step DDIM composition, cfg {wl.cfg}, pnp_f_t {wl.pnp_f_t}, "
+            f"spatial/temporal attn injection {wl.pnp_spatial_attn_t}/{wl.pnp_temp_attn_t}")
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -189,7 +195,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": len(vals), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload + " (bounded CPU sample per step)"},
+        "config": {"workload": workload_description(sampler.full), "parallelism": f"{last[0]} host threads",
+                   "sample_per_step": last[1]},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": last[0], "kind": "port", "sample": last[1]},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -360,10 +367,7 @@ def run_mvoc(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {
-            "workload": f"{wl.name}: full i2vgen-xl UNet random-init, {wl.n_frames} frames x "
-                        f"{wl.latent_h}x{wl.latent_w} latents, bg+{wl.n_obj} objects, {wl.n_steps}-step DDIM "
-                        f"composition, cfg {wl.cfg}, pnp_f_t {wl.pnp_f_t}, spatial/temporal attn injection "
-                        f"{wl.pnp_spatial_attn_t}/{wl.pnp_temp_attn_t}",
+            "workload": workload_description(wl),
             "parallelism": par.describe(),
             "l2": "activations per step (>= 210 MB per l0 tensor) exceed the 126 MB L2; no explicit flush",
             "timed_steps_start_at": 0,
