@@ -58,8 +58,10 @@ int mvoc_device_check(int device);
  * Strides are in ELEMENTS for (batch, token, head).  Tensor-core path
  * (tcgen05.mma, accumulators in TMEM, operands staged by TMA); bf16 only.
  * Requirements: base pointers 16-byte aligned, strides multiples of 8.
- * variant: 0 = default, 1 = force P-through-shared-memory (SS MMA),
- *          2 = force P-in-TMEM (TS MMA).  Same results; used by the tests.
+ * variant: 0 = default (currently 4).  1 = P through shared memory (SS MMA), all exp2 on the MUFU;
+ *          2 = P in TMEM (TS MMA), all exp2 on the MUFU; 3 / 4 / 5 = P in TMEM with 2 / 3 / 4 of every
+ *          8 exp2 pairs evaluated by a degree-3 polynomial on the FMA pipe.  Same results up to the exp2
+ *          approximation (<= 1e-4 relative, below the bf16 rounding of P); the tests run all of them.
  */
 int mvoc_attn_fwd(const void* q, const void* k, const void* v, void* o,
                   int B, int H, int Nq, int Nk, int D,

@@ -141,6 +141,7 @@ class I2VGenXLPipeline:
             fps_emb = unet.fps_embedding(unet.time_proj(cond.fps).to(unet.dtype))
             cache = {"key": cond, "ctx": ctx, "il": il, "fps_emb": fps_emb}
             self._cond_cache = cache
+            self._graphs.clear()         # captured graphs point at the previous conditioning tensors
         if self._t_dev is None:
             self._t_dev = torch.zeros(1, dtype=torch.int64, device=sample.device)
         self._t_dev.fill_(int(t))        # device-side timestep: the captured graph reads it at replay time
@@ -150,7 +151,11 @@ class I2VGenXLPipeline:
         if sample.data_ptr() != static.data_ptr():
             static.copy_(sample)
         sample = static
-        key = (pnp_utils.hook_signature(unet), tuple(sample.shape), id(cond), par.world)
+        # the capture bakes in control flow (which hooks fire) and addresses (input buffer, conditioning cache,
+        # token masks): all of them are part of the key
+        mask = getattr(unet.conv_out, "mask", None)
+        mask_id = tuple((m[0].data_ptr(), m[1].data_ptr()) for m in mask) if mask else ()
+        key = (pnp_utils.hook_signature(unet), tuple(sample.shape), id(cond), par.world, mask_id)
         entry = self._graphs.get(key)
         if entry is None:
             # eager warm-up on a side stream (lazy weight fusions, cuDNN autotune, mask caches), then capture
