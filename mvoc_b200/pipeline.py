@@ -60,6 +60,18 @@ class LatentBank:
     def from_dir(cls, path: str, timesteps: Sequence[int], device, pin_host: bool = False):
         return cls({int(t): load_ddim_latents_at_t(t, path) for t in timesteps}, device, pin_host)
 
+    # packed single-file form of one video's latent store: the per-timestep files stay the
+    # interchange format with the reference, this is the fast path between our own inverse and composite runs
+    def save_packed(self, path: str) -> None:
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        ts = sorted(self.index, key=self.index.get)
+        torch.save({"timesteps": ts, "latents": self.data.detach().cpu()}, path)
+
+    @classmethod
+    def load_packed(cls, path: str, device, pin_host: bool = False) -> "LatentBank":
+        blob = torch.load(path, map_location="cpu")
+        return cls({int(t): blob["latents"][i] for i, t in enumerate(blob["timesteps"])}, device, pin_host)
+
     def at(self, t: int) -> torch.Tensor:
         return self.data[self.index[int(t)]]
 

@@ -405,3 +405,66 @@ def test_cli_parsers_keep_the_reference_flags():
     assert d.template_config == "./configs/group_composite/template.yaml"       # composite.py:229-235
     i = inverse.build_parser().parse_args([])
     assert i.configs_json == "./configs/group_inversion/group_config.json"      # inverse.py:231-235
+
+
+def test_latent_bank_packed_round_trip(tmp_path):
+    from mvoc_b200.pipeline import LatentBank
+
+    data = {t: torch.randn(1, 4, 2, 4, 4) for t in (981, 1, 501)}
+    bank = LatentBank(data, "cpu")
+    p = str(tmp_path / "store" / "bank.pt")
+    bank.save_packed(p)
+    again = LatentBank.load_packed(p, "cpu")
+    assert again.index == bank.index
+    for t in data:
+        assert torch.equal(again.at(t), data[t][0])
+
+
+# ------------------------------------------------------------------ bench.py helpers (no GPU)
+def test_bench_clock_sampler_parsing_and_peaks():
+    import bench
+
+    cs = bench.ClockSampler(0)
+    cs.proc = SimpleNamespace(terminate=lambda: None, wait=lambda timeout=None: 0, kill=lambda: None)
+    cs.lines = ["0, 1657, 1965, 990.12, Not Active, Not Active, Not Active, Active",
+                "0, 1702, 1965, 975.00, Not Active, Not Active, Not Active, Active",
+                "garbage line",
+                "0, 1965, 1965, 300.00, Not Active, Not Active, Not Active, Not Active"]
+    out = cs.stop()
+    assert out["sm_mhz"] == 1702.0 and out["sm_max_mhz"] == 1965.0 and out["samples"] == 3
+    assert out["reasons"] == ["sw_power_cap"]
+    peaks = bench.measured_peaks()
+    assert peaks["hbm_gbs"] > 1000 and peaks["bf16_tflops_sustained"] > 100 and peaks["_source"] in ("measured", "fallback")
+    from mvoc_b200 import synthetic
+
+    d = bench.workload_description(synthetic.WORKLOADS["config2"])
+    assert "16 frames x 64x64" in d and "bg+2 objects" in d and "50-step" in d
+
+
+def test_bench_reference_arm_contract(monkeypatch, capsys):
+    """--impl reference prints the contract keys; non-zero ranks stay silent (the CPU work itself is faked)."""
+    import json
+
+    import bench
+    from mvoc_b200 import synthetic
+
+    class FakeSampler:
+        def __init__(self, wl, budget):
+            self.cores, self.desc, self.full = 4, "fake sample", synthetic.WORKLOADS[wl]
+
+        def step(self):
+            return 0.002, 0.5
+
+    monkeypatch.setattr(bench, "CpuSampler", FakeSampler)
+    args = SimpleNamespace(steps=3, warmup=1, gpus=2, workload="config2")
+    monkeypatch.setenv("RANK", "1")
+    bench.run_reference(args)
+    assert capsys.readouterr().out == ""
+    monkeypatch.setenv("RANK", "0")
+    bench.run_reference(args)
+    line = json.loads(capsys.readouterr().out)
+    assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["higher_is_better"] is True
+    assert line["steps"] == 3 and line["value"] == pytest.approx(0.002)
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 4
+    assert line["e2e"] == {"value": pytest.approx(0.002), "unit": "frames/s", "h2d_bytes_per_step": 0,
+                           "d2h_bytes_per_step": 0}
