@@ -129,8 +129,6 @@ class I2VGenXLPipeline:
                 seen.add(sig)
                 firsts.append(i)
         return firsts
-        self.scheduler: Optional[DDIMSchedule] = None
-        self._cond_cache = None
 
     # ------------------------------------------------------------------ UNet driver
     def _unet_forward(self, sample, t: int, cond: Conditioning):

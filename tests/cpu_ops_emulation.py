@@ -1,0 +1,162 @@
+"""TEST-ONLY emulation of the C-ABI kernel contracts in plain torch (fp32, CPU).
+
+The product (`mvoc_b200/`) has no CPU path: `mvoc_b200.ops` raises on non-CUDA tensors.  To test the HOST
+logic without a GPU — the channels-last UNet wiring, the hook layer, the step loops and the multi-GPU
+partition — the tests in `tests/test_host_pipeline_cpu.py` monkeypatch `mvoc_b200.ops` with the functions
+below, which restate each kernel's documented contract (include/mvoc_b200.h) with the oracle's ops.  Nothing
+under `mvoc_b200/` imports this file.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from oracle import ops_ref
+
+
+def attention(q, k, v, heads, scale=None, out=None, variant=0):
+    o = ops_ref.sdpa_ref(q.contiguous(), k.contiguous(), v.contiguous(), heads)
+    if out is not None:
+        out.copy_(o)
+        return out
+    return o
+
+
+def temporal_attention_frames(q, k, v, heads, B, T, S, scale=None, out=None):
+    C = q.shape[-1]
+
+    def to_ref(x):  # rows (b, t, p) -> [(b p), t, c]
+        return x.reshape(B, T, S, C).permute(0, 2, 1, 3).reshape(B * S, T, C)
+
+    o = ops_ref.sdpa_ref(to_ref(q), to_ref(k), to_ref(v), heads)
+    return o.view(B, S, T, C).permute(0, 2, 1, 3).reshape(B * T * S, C)
+
+
+def temporal_attention(q, k, v, heads, scale=None, out=None):
+    return ops_ref.sdpa_ref(q, k, v, heads)
+
+
+def qk_blend_(q, k, mask, n_obj, inject_background):
+    nb = n_obj + 3
+    base = 0 if inject_background else n_obj + 2
+    for x in (q, k):
+        if x is None:
+            continue
+        C = x.shape[-1]
+        v = x.view(nb, -1, C)
+        acc = v[base].clone()
+        for j in range(n_obj):
+            m = mask[j].to(torch.float32)[:, None]
+            if mask.dtype == torch.uint8:
+                acc = torch.where(m != 0, v[j + 1], acc)
+            else:
+                acc = acc * (1 - m) + v[j + 1] * m
+        v[n_obj + 1] = acc
+        v[n_obj + 2] = acc
+
+
+def feature_blend_(x, mask, n_obj, frames):
+    nb = n_obj + 3
+    v = x.view(nb, frames, x.shape[1], -1)                      # [slot, T, C, HW]
+    acc = v[0].clone()
+    for j in range(n_obj):
+        m = mask[j].bool()[:, None, :]                          # [T, 1, HW]
+        acc = torch.where(m, v[j + 1], acc)
+    v[n_obj + 1] = acc
+    v[n_obj + 2] = acc
+
+
+def groupnorm_nhwc(x, weight, bias, groups, eps, silu, frames_per_stat=1, add=None, out=None, gather=None):
+    """Same three phases as the kernels: per-(n, group) partial (mean, M2) of the local rows, optional gather of
+    the partial sets of other ranks, Chan merge over sets and over the `frames_per_stat` frames, apply."""
+    N, C = x.shape[0], x.shape[-1]
+    cg = C // groups
+    xs = x.reshape(N, -1, C).to(torch.float32)
+    if add is not None:
+        xs = xs + add.to(torch.float32)[:, None, :]
+    S = xs.shape[1]
+    xg = xs.view(N, S, groups, cg)
+    mean = xg.mean(dim=(1, 3))
+    m2 = ((xg - mean[:, None, :, None]) ** 2).sum(dim=(1, 3))
+    partial = torch.stack([mean, m2], dim=-1)[:, :, None, :].contiguous()       # [N, G, 1, 2]
+    sets = partial[None] if gather is None else gather(partial)                # [sets, N, G, 1, 2]
+    cnt = float(S * cg)
+    n_sets = sets.shape[0]
+    pm = sets[..., 0, 0].reshape(n_sets, N // frames_per_stat, frames_per_stat, groups)
+    pq = sets[..., 0, 1].reshape(n_sets, N // frames_per_stat, frames_per_stat, groups)
+    total = cnt * n_sets * frames_per_stat
+    gmean = pm.mean(dim=(0, 2))                                                  # equal counts per partial
+    gm2 = pq.sum(dim=(0, 2)) + cnt * ((pm - gmean[None, :, None, :]) ** 2).sum(dim=(0, 2))
+    rstd = torch.rsqrt(gm2 / total + eps)                                        # [N/frames, G]
+    gmean = gmean.repeat_interleave(frames_per_stat, dim=0)[:, None, :, None]
+    rstd = rstd.repeat_interleave(frames_per_stat, dim=0)[:, None, :, None]
+    y = (xg - gmean) * rstd
+    y = y.reshape(N, S, C) * weight.to(torch.float32) + bias.to(torch.float32)
+    if silu:
+        y = F.silu(y)
+    y = y.to(x.dtype).view(x.shape)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def layernorm(x, weight, bias, eps, out=None):
+    return F.layer_norm(x, (x.shape[-1],), weight, bias, eps)
+
+
+def geglu(x, out=None):
+    a, g = x.chunk(2, dim=-1)
+    return a * F.gelu(g)
+
+
+def latent_composite_(z, bg, objs, mask, unet_in, ratio, do_fusion, obj_noise_fusion=False):
+    n_obj = objs.shape[0]
+    if do_fusion:
+        zz = ratio * z + (1.0 - ratio) * bg.view_as(z)
+        for j in range(n_obj):
+            m = mask[j].view(1, 1, *z.shape[2:]).expand_as(z)
+            obj = objs[j].view_as(z)
+            fg = (zz * m) * ratio + (1 - ratio) * (obj * m) if obj_noise_fusion else obj * m
+            zz = zz * (1.0 - m) + fg
+        z.copy_(zz)
+    if unet_in is not None:
+        unet_in[0].copy_(bg.reshape(unet_in[0].shape))
+        for j in range(n_obj):
+            unet_in[j + 1].copy_(objs[j].reshape(unet_in[0].shape))
+        unet_in[n_obj + 1].copy_(z.reshape(unet_in[0].shape))
+        unet_in[n_obj + 2].copy_(z.reshape(unet_in[0].shape))
+
+
+def _ddim(pu, pc, x, g, a_from, a_to):
+    v = pu.to(torch.float32) if pc is None else pu.to(torch.float32) + g * (pc.to(torch.float32) - pu.to(torch.float32))
+    x.copy_(ops_ref.ddim_step_ref(v.view_as(x), x, a_from, a_to))
+
+
+def cfg_ddim_step_(pred_uncond, pred_cond, x, guidance, alpha_t, alpha_prev):
+    _ddim(pred_uncond, pred_cond, x, guidance, alpha_t, alpha_prev)
+
+
+def ddim_inverse_step_(pred_uncond, pred_cond, x, guidance, alpha_src, alpha_dst):
+    _ddim(pred_uncond, pred_cond, x, guidance, alpha_src, alpha_dst)
+
+
+def install(monkeypatch_or_module=None):
+    """Replace the kernel wrappers of mvoc_b200.ops with the emulations (tests only)."""
+    from mvoc_b200 import ops
+
+    names = ["attention", "temporal_attention_frames", "temporal_attention", "qk_blend_", "feature_blend_",
+             "groupnorm_nhwc", "layernorm", "geglu", "latent_composite_", "cfg_ddim_step_", "ddim_inverse_step_"]
+    saved = {n: getattr(ops, n) for n in names}
+    for n in names:
+        setattr(ops, n, globals()[n])
+    return saved
+
+
+def uninstall(saved):
+    from mvoc_b200 import ops
+
+    for n, f in saved.items():
+        setattr(ops, n, f)
