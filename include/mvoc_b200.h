@@ -42,6 +42,10 @@ extern "C" {
 #define MVOC_MASK_U8 0  /* binary select, bit exact  */
 #define MVOC_MASK_F32 1 /* soft mask, fp32 lerp, rounded once */
 
+/* modes of mvoc_attn_inject_fwd */
+#define MVOC_INJECT_SPATIAL 0  /* attention over the pixels of each (branch, frame) */
+#define MVOC_INJECT_TEMPORAL 1 /* attention over the frames of each (branch, pixel) */
+
 const char* mvoc_version(void);
 const char* mvoc_last_error(void);
 /* 0 if `device` is compute capability 10.x, MVOC_ERR_UNSUPPORTED otherwise. */
@@ -115,6 +119,25 @@ int mvoc_attn_temporal_strided_fwd(const void* q, const void* k, const void* v, 
 int mvoc_qk_blend(void* x0, void* x1, int n_obj, int64_t tokens, int C,
                   const void* mask, int mask_kind, int base_slot,
                   int dtype, void* stream);
+
+/*
+ * Injected self-attention in one call: mvoc_qk_blend followed by the attention of ALL branches on `stream`.
+ * Replaces what ModifiedSpaAttnProcessor.__call__ does between the q/k/v projections and to_out
+ * (i2vgen-xl/pnp_utils.py:624-686; mode MVOC_INJECT_SPATIAL, binary mask) and what
+ * ModifiedTmpAttnProcessor.__call__ does there (:778-864; mode MVOC_INJECT_TEMPORAL, float mask).
+ *
+ * q, k, v, o: contiguous [(n_obj+3)*frames, pixels, H*D] — rows in (branch, frame, pixel) order in BOTH
+ * modes (the temporal mode reads the frames of a pixel through strides; the [(b h w), T, C] permute of
+ * :189 is not needed).  q and k are modified in place exactly like mvoc_qk_blend (slots n_obj+1, n_obj+2).
+ * mask: [n_obj, frames*pixels] in (frame, pixel) order, kind as for mvoc_qk_blend.
+ * Restrictions of the attention kernels apply (D == 64, bf16; temporal: frames <= 32).
+ * share_p: reserved for computing one softmax for the uncond/cond pair (they share Q', K' after the
+ * injection, :664-668); must be 0, anything else returns MVOC_ERR_UNSUPPORTED.
+ * Today this is two launches; it is the seam behind which the blend moves into the attention kernel.
+ */
+int mvoc_attn_inject_fwd(void* q, void* k, const void* v, void* o, int n_obj, int frames, int64_t pixels,
+                         int H, int D, const void* mask, int mask_kind, int base_slot, int mode,
+                         int share_p, float scale, int dtype, int variant, void* stream);
 
 /*
  * Hidden-state mask-blend after resnet conv2 / temporal conv / conv_out.

@@ -203,6 +203,44 @@ def qk_blend_(
     _count()
 
 
+def attention_inject_(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask: torch.Tensor, heads: int, n_obj: int,
+                      frames: int, inject_background: bool, temporal: bool, scale: Optional[float] = None,
+                      out: Optional[torch.Tensor] = None, variant: int = 0) -> torch.Tensor:
+    """Q/K injection + attention of all branches through the single C-ABI call mvoc_attn_inject_fwd.
+    q, k, v: contiguous [(n_obj+3)*frames, pixels, H*64], rows in (branch, frame, pixel) order for the spatial
+    AND the temporal mode; mask [n_obj, frames*pixels] uint8 / float32.  q and k are modified in place."""
+    _need_cuda(q, k, v, mask, out)
+    nb = n_obj + 3
+    if q.dim() != 3 or q.shape[0] != nb * frames or k.shape != q.shape or v.shape != q.shape:
+        raise ValueError(f"attention_inject_: need q, k, v [{nb}*{frames}, pixels, C], got {tuple(q.shape)}")
+    if not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()):
+        raise ValueError("attention_inject_: q, k, v must be contiguous")
+    pixels, C = q.shape[1], q.shape[2]
+    if C != heads * HEAD_DIM:
+        raise ValueError(f"attention_inject_: C={C} != heads*{HEAD_DIM}")
+    if mask.dtype == torch.uint8:
+        kind = MVOC_MASK_U8
+    elif mask.dtype == torch.float32:
+        kind = MVOC_MASK_F32
+    else:
+        raise TypeError(f"attention_inject_: mask dtype {mask.dtype} (need uint8 or float32)")
+    if tuple(mask.shape) != (n_obj, frames * pixels) or not mask.is_contiguous():
+        raise ValueError(f"attention_inject_: mask must be contiguous [{n_obj}, {frames * pixels}]")
+    if out is None:
+        out = torch.empty_like(q)
+    elif out.shape != q.shape or not out.is_contiguous():
+        raise ValueError("attention_inject_: out must be contiguous and shaped like q")
+    if scale is None:
+        scale = HEAD_DIM ** -0.5
+    base = 0 if inject_background else n_obj + 2
+    rc = _cabi.load().mvoc_attn_inject_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), n_obj, frames,
+                                           pixels, heads, HEAD_DIM, mask.data_ptr(), kind, base, int(bool(temporal)),
+                                           0, float(scale), _dt(q), int(variant), _stream())
+    _cabi.check(rc, "mvoc_attn_inject_fwd")
+    _count(2)
+    return out
+
+
 def feature_blend_(x: torch.Tensor, mask: torch.Tensor, n_obj: int, frames: int) -> None:
     """In-place hidden-state injection on x [n_branches*T, C, H, W]; mask [n_obj, T, H*W] uint8."""
     _need_cuda(x, mask)

@@ -40,6 +40,15 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc == -1 and b"n_obj" in lib.mvoc_last_error()
     rc = lib.mvoc_cfg_ddim_step(16, 16, 16, 7, 1.0, 0.5, 0.6, 0, 2, None)
     assert rc == -2 and b"multiple of 8" in lib.mvoc_last_error()
+    inj = lambda **kw: lib.mvoc_attn_inject_fwd(*[{**dict(q=16, k=16, v=16, o=16, n_obj=2, frames=2, pixels=256, H=2, D=64,
+                                                          mask=16, kind=0, base=4, mode=0, share_p=0, scale=0.125,
+                                                          dtype=0, variant=0, stream=None), **kw}[n] for n in
+                                                  ("q", "k", "v", "o", "n_obj", "frames", "pixels", "H", "D", "mask", "kind",
+                                                   "base", "mode", "share_p", "scale", "dtype", "variant", "stream")])
+    assert inj(q=None) == -1 and b"null pointer" in lib.mvoc_last_error()
+    assert inj(n_obj=0) == -1 and b"n_obj" in lib.mvoc_last_error()
+    assert inj(mode=2) == -1 and b"mode" in lib.mvoc_last_error()
+    assert inj(share_p=1) == -2 and b"share_p" in lib.mvoc_last_error()
 
 
 def test_product_ops_refuse_cpu_tensors():

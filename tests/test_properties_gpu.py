@@ -168,3 +168,42 @@ def test_ddim_round_trip_and_composite_identity_full_size(cuda_device):
     assert torch.equal(z, z0)
     assert torch.equal(unet_in[0], bg[0].bfloat16()) and torch.equal(unet_in[1:3], objs.bfloat16())
     assert torch.equal(unet_in[3], z0[0].bfloat16()) and torch.equal(unet_in[4], z0[0].bfloat16())
+
+
+@pytest.mark.parametrize("temporal", [False, True])
+def test_attn_inject_entry_equals_blend_then_attention(cuda_device, temporal):
+    """mvoc_attn_inject_fwd (one C-ABI call) == mvoc_qk_blend followed by the attention entry point, bit for bit,
+    and agrees with the fp32 oracle ops.  (Entry point added after the last GPU session of round 1: this test is
+    its first run on hardware.)"""
+    from mvoc_b200 import ops
+    from oracle import ops_ref
+    from tests import cpu_ops_emulation as emu
+
+    g = torch.Generator(device=cuda_device).manual_seed(6)
+    n_obj, frames, pixels, heads = 2, 4, 256, 2
+    nb, C = n_obj + 3, heads * 64
+    q, k, v = (torch.randn(nb * frames, pixels, C, device=cuda_device, generator=g).bfloat16() for _ in range(3))
+    m = torch.rand(n_obj, frames * pixels, device=cuda_device, generator=g)
+    mask = m.clamp(0, 1).contiguous() if temporal else (m < 0.1).to(torch.uint8)
+    # two validated calls
+    q2, k2 = q.clone(), k.clone()
+    ops.qk_blend_(q2, k2, mask, n_obj, False)
+    if temporal:
+        ref = ops.temporal_attention_frames(q2.view(-1, C), k2.view(-1, C), v.view(-1, C), heads, nb, frames, pixels).view_as(q)
+    else:
+        ref = ops.attention(q2, k2, v, heads)
+    # the single entry point
+    q1, k1 = q.clone(), k.clone()
+    out = ops.attention_inject_(q1, k1, v, mask, heads, n_obj, frames, False, temporal)
+    torch.cuda.synchronize()
+    assert torch.equal(q1, q2) and torch.equal(k1, k2)
+    assert torch.equal(out, ref)
+    # fp32 oracle on the same bf16-rounded inputs
+    qc, kc, vc = q.float().cpu(), k.float().cpu(), v.float().cpu()
+    emu.qk_blend_(qc, kc, mask.cpu(), n_obj, False)
+    if temporal:
+        want = emu.temporal_attention_frames(qc.view(-1, C), kc.view(-1, C), vc.view(-1, C), heads, nb, frames, pixels).view_as(qc)
+    else:
+        want = ops_ref.sdpa_ref(qc, kc, vc, heads)
+    rel = ((out.float().cpu() - want).norm() / want.norm()).item()
+    assert rel <= 1e-2, rel
