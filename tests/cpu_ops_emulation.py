@@ -16,7 +16,17 @@ import torch.nn.functional as F
 from oracle import ops_ref
 
 
+def _rows_ok(t, heads):
+    """The layout the real wrappers accept: [.., heads*64] with a contiguous last dim and 16-byte-aligned rows."""
+    assert t.shape[-1] == heads * 64 and t.stride(-1) == 1, (tuple(t.shape), t.stride())
+    assert all(s % 8 == 0 for s in t.stride()[:-1]), t.stride()
+
+
 def attention(q, k, v, heads, scale=None, out=None, variant=0):
+    for t in (q, k, v):
+        assert t.dim() == 3
+        _rows_ok(t, heads)
+    assert k.shape[0] == q.shape[0] and v.shape == k.shape
     o = ops_ref.sdpa_ref(q.contiguous(), k.contiguous(), v.contiguous(), heads)
     if out is not None:
         out.copy_(o)
@@ -26,6 +36,9 @@ def attention(q, k, v, heads, scale=None, out=None, variant=0):
 
 def temporal_attention_frames(q, k, v, heads, B, T, S, scale=None, out=None):
     C = q.shape[-1]
+    for t in (q, k, v):
+        assert t.dim() == 2 and t.shape[0] == B * T * S and T <= 32
+        _rows_ok(t, heads)
 
     def to_ref(x):  # rows (b, t, p) -> [(b p), t, c]
         return x.reshape(B, T, S, C).permute(0, 2, 1, 3).reshape(B * S, T, C)
@@ -41,6 +54,8 @@ def temporal_attention(q, k, v, heads, scale=None, out=None):
 def qk_blend_(q, k, mask, n_obj, inject_background):
     nb = n_obj + 3
     base = 0 if inject_background else n_obj + 2
+    assert q.is_contiguous() and (k is None or k.is_contiguous()) and mask.is_contiguous()
+    assert mask.dtype in (torch.uint8, torch.float32) and tuple(mask.shape) == (n_obj, q.numel() // (nb * q.shape[-1]))
     for x in (q, k):
         if x is None:
             continue
@@ -59,6 +74,8 @@ def qk_blend_(q, k, mask, n_obj, inject_background):
 
 def feature_blend_(x, mask, n_obj, frames):
     nb = n_obj + 3
+    assert x.dim() == 4 and x.is_contiguous() and x.shape[0] == nb * frames
+    assert mask.dtype == torch.uint8 and tuple(mask.shape) == (n_obj, frames, x.shape[2] * x.shape[3])
     v = x.view(nb, frames, x.shape[1], -1)                      # [slot, T, C, HW]
     acc = v[0].clone()
     for j in range(n_obj):
@@ -72,6 +89,8 @@ def groupnorm_nhwc(x, weight, bias, groups, eps, silu, frames_per_stat=1, add=No
     """Same three phases as the kernels: per-(n, group) partial (mean, M2) of the local rows, optional gather of
     the partial sets of other ranks, Chan merge over sets and over the `frames_per_stat` frames, apply."""
     N, C = x.shape[0], x.shape[-1]
+    assert x.is_contiguous() and C % groups == 0 and N % frames_per_stat == 0
+    assert add is None or (tuple(add.shape) == (N, C) and add.is_contiguous() and add.dtype == x.dtype)
     cg = C // groups
     xs = x.reshape(N, -1, C).to(torch.float32)
     if add is not None:
@@ -104,10 +123,12 @@ def groupnorm_nhwc(x, weight, bias, groups, eps, silu, frames_per_stat=1, add=No
 
 
 def layernorm(x, weight, bias, eps, out=None):
+    assert x.is_contiguous()
     return F.layer_norm(x, (x.shape[-1],), weight, bias, eps)
 
 
 def geglu(x, out=None):
+    assert x.is_contiguous() and x.shape[-1] % 16 == 0
     a, g = x.chunk(2, dim=-1)
     return a * F.gelu(g)
 
