@@ -25,6 +25,7 @@ from __future__ import annotations
 
 import inspect
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -83,9 +84,37 @@ class _Ctx:
         self.full_hw = None    # (h, w) of the un-sharded frame while a temporal operator runs on pixel shards
 
 
-def conv_nhwc(x: torch.Tensor, conv: nn.Conv2d, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+# MVOC_STAGED=1 routes the stride-1 3x3 convolutions and the GEGLU projection through the tcgen05 kernels staged
+# in libmvoc_b200_staged.so (include/mvoc_b200_staged.h).  Off by default: those kernels have not been validated
+# on hardware yet, the measured product path is cuDNN / cuBLAS + mvoc_geglu.
+_STAGED = os.environ.get("MVOC_STAGED") == "1"
+
+
+def _staged_conv_ok(conv: nn.Conv2d) -> bool:
+    return (conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1)
+            and conv.dilation == (1, 1) and conv.groups == 1 and conv.in_channels % 64 == 0
+            and conv.out_channels % 64 == 0)
+
+
+def _staged_conv(x, conv, bias=None, residual=None):
+    from . import staged
+
+    wt = conv.__dict__.get("_w_taps")
+    if wt is None or wt.device != x.device or wt.dtype != x.dtype:
+        wt = staged.prepare_conv_weight(conv.weight.detach()).to(x.dtype)
+        conv.__dict__["_w_taps"] = wt
+    return staged.conv3x3_nhwc(x, wt, conv.bias if bias is None else bias, residual)
+
+
+def conv_nhwc(x: torch.Tensor, conv: nn.Conv2d, bias: Optional[torch.Tensor] = None,
+              residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """3x3 / strided conv on a channels-last activation [N, H, W, C] -> [N, H', W', C'] (cuDNN NHWC kernels:
-    the permuted view IS torch's channels_last memory format, so no nchw<->nhwc conversion runs)."""
+    the permuted view IS torch's channels_last memory format, so no nchw<->nhwc conversion runs).
+    `residual` (same shape as the result) is added to it."""
+    if _STAGED and _staged_conv_ok(conv):
+        return _staged_conv(x, conv, bias, residual)
+    if residual is not None:
+        return conv_nhwc(x, conv, bias).add_(residual)
     y = F.conv2d(x.permute(0, 3, 1, 2), conv.weight, conv.bias if bias is None else bias, conv.stride, conv.padding)
     y = y.permute(0, 2, 3, 1)
     return y if y.is_contiguous() else y.contiguous()
@@ -238,6 +267,10 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
     def forward(self, x):
+        if _STAGED and self.proj.in_features % 64 == 0 and self.proj.out_features % 128 == 0:
+            from . import staged
+
+            return staged.linear_geglu(x, self.proj.weight, self.proj.bias)
         return ops.geglu(self.proj(x))      # x * gelu(gate) in one pass (mvoc_geglu)
 
 
@@ -377,10 +410,11 @@ class ResnetBlock2D(nn.Module):
         t = self.time_emb_proj(F.silu(temb))                                    # :941-948
         h = self.norm2(h, silu=True, add=t, out=h)                              # `+ temb` :952 fused into norm2 :953, :965
         if self.conv_shortcut is None:
+            if self.feature_hook is None:
+                return conv_nhwc(h, self.conv2, residual=input_tensor)          # :968 + :1018 (scale factor 1)
             h = conv_nhwc(h, self.conv2)                                        # :968
-            if self.feature_hook is not None:
-                self.feature_hook(self, h)                                      # :970-1004
-            return h.add_(input_tensor)                                         # :1018 (scale factor 1)
+            self.feature_hook(self, h)                                          # :970-1004
+            return h.add_(input_tensor)                                         # :1018
         # 1x1 shortcut conv (:1011-1016) == row GEMM accumulated into conv2's output; its bias rides on
         # conv2's (a per-channel constant commutes with the per-pixel select of the injection)
         if self._bias2 is None or self._bias2.device != h.device or self._bias2.dtype != h.dtype:

@@ -171,3 +171,41 @@ def test_host_composite_frame_parallel(world):
         assert status == "ok", f"rank {r}: {err}"
         assert err <= TOL, f"rank {r}: sharded vs single {err:.3e}"
         assert same, "ranks disagree on the updated latents"
+
+
+def test_host_staged_routing_vs_oracle(emulated_ops, monkeypatch):
+    """MVOC_STAGED=1 routing (stride-1 3x3 convolutions with tap-major weights and the fused residual, GEGLU
+    projection) with the staged kernels emulated in torch: same composition result as the oracle."""
+    import torch.nn.functional as F
+
+    from mvoc_b200 import staged, unet3d
+    from oracle import pipeline as opipe
+
+    calls = {"conv": 0, "conv_res": 0, "geglu": 0}
+
+    def conv3x3_nhwc(x, w_taps, bias=None, residual=None, out=None, variant=0):
+        co, ci = w_taps.shape[1], w_taps.shape[2]
+        assert x.is_contiguous() and w_taps.is_contiguous() and ci % 64 == 0 and co % 64 == 0
+        w = w_taps.view(3, 3, co, ci).permute(2, 3, 0, 1)
+        y = F.conv2d(x.permute(0, 3, 1, 2), w, bias, padding=1).permute(0, 2, 3, 1).contiguous()
+        calls["conv"] += 1
+        if residual is not None:
+            assert residual.shape == y.shape and residual.is_contiguous()
+            calls["conv_res"] += 1
+            y += residual
+        return y
+
+    def linear_geglu(x, weight, bias=None, out=None):
+        assert x.is_contiguous()
+        calls["geglu"] += 1
+        v, g = F.linear(x, weight, bias).chunk(2, dim=-1)
+        return v * F.gelu(g)
+
+    monkeypatch.setattr(unet3d, "_STAGED", True)
+    monkeypatch.setattr(staged, "conv3x3_nhwc", conv3x3_nhwc)
+    monkeypatch.setattr(staged, "linear_geglu", linear_geglu)
+    wl, sched, inputs, ou = _setup("reduced2")
+    ref = opipe.composite_loop(copy.deepcopy(ou), wl, inputs, max_steps=2)
+    out = _composite(wl, sched, inputs, _product_cpu(ou, wl.unet), 2)
+    assert rel_l2(out, ref) <= TOL
+    assert calls["conv"] > 0 and calls["conv_res"] > 0 and calls["geglu"] > 0

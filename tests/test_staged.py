@@ -1,0 +1,85 @@
+"""Kernels staged for the next round (include/mvoc_b200_staged.h).  CPU: the separate library loads, exports what
+its header declares, and validates arguments.  The numerics tests run only on a GPU with MVOC_STAGED=1 — they are
+NOT part of the `-m gpu` suite because the kernels have not run on hardware yet."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+needs_staged_gpu = pytest.mark.skipif(os.environ.get("MVOC_STAGED") != "1" or not torch.cuda.is_available(),
+                                      reason="staged kernels: set MVOC_STAGED=1 on a B200")
+
+
+def test_staged_library_exports_its_header():
+    from mvoc_b200 import staged
+
+    hdr = open(os.path.join(ROOT, "include", "mvoc_b200_staged.h")).read()
+    declared = set(re.findall(r"\b(mvoc_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(staged.SIGNATURES)
+    lib = staged.load()
+    for name in declared:
+        assert hasattr(lib, name)
+
+
+def test_staged_argument_errors():
+    from mvoc_b200 import staged
+
+    lib = staged.load()
+    assert lib.mvoc_conv3x3_nhwc(None, None, None, None, None, 1, 8, 8, 64, 64, 0, 0, None) == -1
+    assert b"null pointer" in lib.mvoc_last_error()
+    assert lib.mvoc_conv3x3_nhwc(16, 16, None, None, 16, 1, 8, 8, 48, 64, 0, 0, None) == -2
+    assert b"multiples of 64" in lib.mvoc_last_error()
+    assert lib.mvoc_conv3x3_nhwc(16, 16, None, None, 16, 1, 8, 8, 64, 64, 1, 0, None) == -2      # fp16
+    assert lib.mvoc_linear_geglu(16, 16, None, 16, 128, 100, 64, 0, None) == -2
+    assert b"K=100" in lib.mvoc_last_error()
+    w = torch.randn(6, 5, 3, 3)
+    wt = staged.prepare_conv_weight(w)
+    assert wt.shape == (9, 6, 5) and torch.equal(wt[1 * 3 + 2], w[:, :, 1, 2])
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).norm() / b.float().norm())
+
+
+@needs_staged_gpu
+@pytest.mark.parametrize("shape", [
+    (2, 64, 64, 64, 64),      # N, H, W, Cin, Cout: 2x64 box, BN 64
+    (4, 32, 32, 128, 128),    # 4x32 box, BN 128
+    (16, 8, 8, 128, 160),     # 2 frames per box, BN 160
+    (3, 16, 16, 64, 320),     # BN 320 (two MMA pieces) and BN 160 via variant 1; N not a multiple of the box
+    (2, 11, 20, 64, 64),      # ragged H, W (config 5's lowest level): zero-filled pixels, masked stores
+])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_conv3x3_vs_torch(shape, variant):
+    from mvoc_b200 import staged
+
+    N, H, W, ci, co = shape
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(N, H, W, ci, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(co, ci, 3, 3, device="cuda", generator=g) * (9 * ci) ** -0.5).bfloat16()
+    b = torch.randn(co, device="cuda", generator=g).bfloat16()
+    res = torch.randn(N, H, W, co, device="cuda", generator=g).bfloat16()
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=1).permute(0, 2, 3, 1)
+    out = staged.conv3x3_nhwc(x, staged.prepare_conv_weight(w), b, None, variant=variant)
+    out_r = staged.conv3x3_nhwc(x, staged.prepare_conv_weight(w), b, res, variant=variant)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) <= 5e-3
+    assert _rel(out_r, ref + res.float()) <= 5e-3
+
+
+@needs_staged_gpu
+@pytest.mark.parametrize("M,K,F", [(256, 64, 64), (1000, 320, 1280), (4096, 640, 2560), (300, 128, 192)])
+def test_linear_geglu_vs_torch(M, K, F):
+    from mvoc_b200 import staged
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(2 * F, K, device="cuda", generator=g) * K ** -0.5).bfloat16()
+    b = torch.randn(2 * F, device="cuda", generator=g).bfloat16()
+    y = torch.nn.functional.linear(x.float(), w.float(), b.float())
+    ref = y[:, :F] * torch.nn.functional.gelu(y[:, F:])
+    out = staged.linear_geglu(x, w, b)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) <= 5e-3
