@@ -169,10 +169,13 @@ def install(monkeypatch_or_module=None):
     from mvoc_b200 import ops
 
     names = ["attention", "temporal_attention_frames", "temporal_attention", "qk_blend_", "feature_blend_",
-             "groupnorm_nhwc", "layernorm", "geglu", "latent_composite_", "cfg_ddim_step_", "ddim_inverse_step_"]
+             "layernorm", "geglu", "latent_composite_", "cfg_ddim_step_", "ddim_inverse_step_"]
     saved = {n: getattr(ops, n) for n in names}
     for n in names:
         setattr(ops, n, globals()[n])
+    # ops.groupnorm_nhwc itself (the slab-slicing wrapper) stays real; the kernel-calling piece is emulated
+    saved["_groupnorm_nhwc_slab"] = ops._groupnorm_nhwc_slab
+    ops._groupnorm_nhwc_slab = groupnorm_nhwc
     return saved
 
 

@@ -209,3 +209,26 @@ def test_host_staged_routing_vs_oracle(emulated_ops, monkeypatch):
     out = _composite(wl, sched, inputs, _product_cpu(ou, wl.unet), 2)
     assert rel_l2(out, ref) <= TOL
     assert calls["conv"] > 0 and calls["conv_res"] > 0 and calls["geglu"] > 0
+
+
+def test_host_groupnorm_slabs_vs_oracle(emulated_ops, monkeypatch):
+    """MVOC_GN_SLAB_MB: GroupNorm issued slab by slab (whole statistic groups per slab, in-place and fused-add
+    variants included) gives the same composition result."""
+    from mvoc_b200 import ops
+    from oracle import pipeline as opipe
+
+    slabs = []
+    real = ops._groupnorm_nhwc_slab
+
+    def spy(x, *a, **k):
+        slabs.append(x.shape[0])
+        return real(x, *a, **k)
+
+    monkeypatch.setattr(ops, "_groupnorm_nhwc_slab", spy)
+    monkeypatch.setattr(ops, "_GN_SLAB_BYTES", 96 * 1024)      # a few frames of the reduced model per slab
+    wl, sched, inputs, ou = _setup("reduced2")
+    ref = opipe.composite_loop(copy.deepcopy(ou), wl, inputs, max_steps=2)
+    out = _composite(wl, sched, inputs, _product_cpu(ou, wl.unet), 2)
+    assert rel_l2(out, ref) <= TOL
+    full = wl.n_branches * wl.n_frames
+    assert any(n < full for n in slabs), "no call was split into slabs"

@@ -3,7 +3,7 @@
 # timeout so that a hang costs minutes, not the budget (round 1 lost ~98 GPU-minutes to two multi-rank runs
 # that hung at exit under a 600 s limit).  Usage, from the build container:
 #
-#   gpurun --timeout 1500 -- 'bash tools/gpu_session.sh r02'
+#   gpurun --timeout 2400 -- 'bash tools/gpu_session.sh r02'
 #
 # Output: gpurun_out/<tag>_*  (copy what should be judged into profiles/).
 set -u
@@ -30,4 +30,12 @@ run 240 ncu_attn     ncu --set full --clock-control none --import-source on -k r
 run 420 ncu_launches ncu --metrics gpu__time_duration.sum --clock-control none --nvtx \
                          --nvtx-include "mvoc_timed_region/" --csv --log-file "$OUT/${TAG}_launches_timed_step.csv" \
                          python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graphs
+# ---- options that were staged without hardware: numerics first, then A/B bench lines (K=10 each)
+MVOC_STAGED=1 run 300 staged_tests  python -m pytest tests/test_staged.py -x -q
+MVOC_GN_SLAB_MB=24 run 150 bench_gnslab24 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+MVOC_GN_SLAB_MB=48 run 150 bench_gnslab48 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+if grep -q "passed" "$OUT/${TAG}_staged_tests.log" && ! grep -q "failed" "$OUT/${TAG}_staged_tests.log"; then
+    MVOC_STAGED=1 run 420 staged_pytest_gpu python -m pytest tests -m gpu -x -q
+    MVOC_STAGED=1 run 150 bench_staged python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+fi
 echo "== done" | tee -a "$OUT/${TAG}_session.log"
