@@ -111,7 +111,7 @@ def composite_loop(unet, wl, inputs: dict, max_steps: Optional[int] = None, reco
     init_pnp(pipe, timesteps_full, wl)
     timesteps = timesteps_full[wl.ddim_init_latents_t_idx:]  # :1554
     n_obj = wl.n_obj
-    obj_offsets = [0] * n_obj  # obj_ddim_latents_idx_offset (template.yaml:61)
+    obj_offsets = list(getattr(wl, "obj_ddim_latents_idx_offset", None) or [0] * n_obj)  # template.yaml:61
     fusion_steps = tuple(wl.fusion_step)
     obj_fusion_timesteps = [[int(timesteps_full[obj_offsets[i]:][j]) for j in range(*fusion_steps)]
                             for i in range(n_obj)]  # :1560-1566

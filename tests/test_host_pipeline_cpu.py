@@ -232,3 +232,53 @@ def test_host_groupnorm_slabs_vs_oracle(emulated_ops, monkeypatch):
     assert rel_l2(out, ref) <= TOL
     full = wl.n_branches * wl.n_frames
     assert any(n < full for n in slabs), "no call was split into slabs"
+
+
+# ------------------------------------------------------------------ the reference's own step loops (golden)
+@pytest.mark.parametrize("case", ["default", "exotic"])
+def test_host_composition_loop_vs_reference_golden(emulated_ops, case):
+    """Product loop (host layer in fp32, kernels emulated) against the latents the REFERENCE'S OWN composition loop
+    produced (tests/golden/make_golden_loops.py) — every loop option off its default in the `exotic` case."""
+    from mvoc_b200.pipeline import Conditioning, I2VGenXLPipeline, LatentBank, init_pnp
+    from mvoc_b200.scheduler import DDIMSchedule
+    from tests.golden import spec
+
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "composition_loop_tiny4.pt"), map_location="cpu")
+    fx = spec.loop_fixture(case)
+    wl = spec.loop_workload(fx)
+    inp = spec.loop_inputs(fx, gold["seam"])
+    sched = DDIMSchedule(fx["n_steps"])
+    pipe = I2VGenXLPipeline(_product_cpu(spec.build_tiny4(seed=0), "tiny4"), "cpu")
+    init_pnp(pipe, sched, wl)
+    banks = [LatentBank(src, "cpu", pin_host=False) for src in inp["source_latents"]]
+    rec = {}
+    pipe.sample_with_pnp_pipeline_with_edit_prompt_extraction_with_attn_injection(
+        Conditioning(inp["prompt_embeds"], inp["image_embeddings"], inp["image_latents_first"], inp["image_latents"],
+                     inp["fps"]),
+        inp["init_latents"].clone(), banks[0], banks[1:], inp["masks"], num_inference_steps=fx["n_steps"],
+        guidance_scale=fx["cfg"], ddim_init_latents_t_idx=fx["ddim_init_latents_t_idx"],
+        fusion_steps=tuple(fx["fusion_step"]), random_noise_ratio=fx["random_noise_ratio"],
+        obj_random_noise_fusion=fx["obj_random_noise_fusion"],
+        obj_ddim_latents_idx_offset=fx["obj_ddim_latents_idx_offset"], max_steps=10,
+        callback=lambda i, t, lat: rec.__setitem__(i, lat.clone()))
+    checked = 0
+    for i, ref in gold["latents_after_step"][case].items():
+        if i in rec:
+            assert rel_l2(rec[i], ref) <= TOL, f"{case} step {i}: {rel_l2(rec[i], ref):.3e}"
+            checked += 1
+    assert checked >= 5
+
+
+def test_host_inversion_loop_vs_reference_golden(emulated_ops):
+    from mvoc_b200.pipeline import I2VGenXLPipeline
+    from tests.golden import spec
+
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "inversion_loop_tiny4.pt"), map_location="cpu")
+    ix = spec.inversion_fixture()
+    seam = gold["seam"]
+    pipe = I2VGenXLPipeline(_product_cpu(spec.build_tiny4(seed=0), "tiny4"), "cpu")
+    saved = pipe.invert(spec.inversion_init_latents(ix), seam["encoder_hidden_states"], seam["image_embeddings"],
+                        seam["image_latents"], seam["fps"], num_inference_steps=ix["n_steps"], max_steps=3)
+    assert sorted(saved) == [1, 3, 5]
+    for t in saved:
+        assert rel_l2(saved[t], gold["latents_at_t"][t]) <= TOL

@@ -64,3 +64,48 @@ def test_wire_format_fixture():
     assert ddim_latents_filename(torch.tensor(981)) == "ddim_latents_981.pt"
     x = load_ddim_latents_at_t(981, d)
     assert x.shape == (1, 4, 4, 8, 8) and x.dtype == torch.float16
+
+
+# ---------------------------------------------------------------- step loops run by the reference's own code
+LOOPS = os.path.join(os.path.dirname(__file__), "golden", "composition_loop_tiny4.pt")
+INVERSION = os.path.join(os.path.dirname(__file__), "golden", "inversion_loop_tiny4.pt")
+
+
+LONG = os.environ.get("MVOC_LONG_TESTS") == "1"    # full 50-step / 500-step runs (2-3 minutes); default: first steps
+
+
+@pytest.mark.parametrize("case,max_steps", [("default", 50 if LONG else 10), ("exotic", 10)])
+def test_oracle_reproduces_reference_composition_loop(case, max_steps):
+    """oracle.pipeline.composite_loop == the reference's sample_with_pnp_pipeline_with_edit_prompt_extraction_
+    with_attn_injection (pipeline_i2vgen_xl.py:1552-1734, run by tests/golden/make_golden_loops.py): timestep and
+    fusion-timestep selection, noise fusion, branch concat, hooks per step, CFG, DDIM update."""
+    gold = torch.load(LOOPS, map_location="cpu")
+    fx = spec.loop_fixture(case)
+    rec = []
+    opipe.composite_loop(spec.build_tiny4(seed=0), spec.loop_workload(fx), spec.loop_inputs(fx, gold["seam"]),
+                         max_steps=max_steps, record=rec)
+    checked = 0
+    for i, ref in gold["latents_after_step"][case].items():
+        if i < len(rec):
+            err = float((rec[i] - ref).norm() / ref.norm())
+            assert err <= 1e-5, f"{case} step {i}: {err:.3e}"
+            checked += 1
+    assert checked >= 5
+
+
+def test_oracle_reproduces_reference_inversion_loop():
+    """oracle.pipeline.invert_loop == the reference's invert (pipeline_i2vgen_xl.py:1914-2003); all 500 steps with MVOC_LONG_TESTS=1."""
+    gold = torch.load(INVERSION, map_location="cpu")
+    ix = spec.inversion_fixture()
+    seam = gold["seam"]
+    inv = {"latents": spec.inversion_init_latents(ix), "prompt_embeds": seam["encoder_hidden_states"],
+           "image_embeddings": seam["image_embeddings"], "image_latents": seam["image_latents"], "fps": seam["fps"]}
+    saved = opipe.invert_loop(spec.build_tiny4(seed=0), None, inv, n_steps=ix["n_steps"], max_steps=None if LONG else 3)
+    assert len(saved) == (500 if LONG else 3)
+    checked = 0
+    for t, ref in gold["latents_at_t"].items():
+        if t in saved:
+            err = float((saved[t] - ref).norm() / ref.norm())
+            assert err <= 1e-5, f"t={t}: {err:.3e}"
+            checked += 1
+    assert checked >= 3
