@@ -119,9 +119,30 @@ class FrameParallel:
         k, tl = x.shape[0], x.shape[1]
         return out.permute(1, 0, 2, *range(3, out.dim())).contiguous().view(k, self.world * tl, *x.shape[2:])
 
+    # ------------------------------------------------------------------ temporal operators, replicated
+    # When a level's h*w does not divide by the number of ranks (config 5's 11x20 level on 8 GPUs) — or is at
+    # most MVOC_FP_GATHER_MAX_PIXELS (off by default; the low-resolution levels are latency-bound) — the frames
+    # are all-gathered instead, every rank runs the temporal operator on all pixels and keeps its own frames:
+    # one collective instead of two, no GroupNorm statistics exchange, P-fold redundant work on a small tensor.
+    _GATHER_MAX_PIXELS = int(os.environ.get("MVOC_FP_GATHER_MAX_PIXELS", "0") or 0)
+
+    def _replicate(self, h: int, w: int) -> bool:
+        return (h * w) % self.world != 0 or h * w <= self._GATHER_MAX_PIXELS
+
+    def _temporal_replicated(self, module, hidden_states: torch.Tensor, num_frames: int) -> torch.Tensor:
+        btl, h, w, C = hidden_states.shape
+        tl = num_frames // self.world
+        b = btl // tl
+        full = self.gather_frames(hidden_states.contiguous().view(b, tl, h, w, C)).view(b * num_frames, h, w, C)
+        y = module.forward_local(full, num_frames, None)
+        f0, f1 = self.frame_range(num_frames)
+        return y.view(b, num_frames, h, w, C)[:, f0:f1].contiguous().view(b * tl, h, w, C)
+
     # ------------------------------------------------------------------ temporal operators on pixel shards
     def temporal_transformer(self, module, hidden_states: torch.Tensor, num_frames: int) -> torch.Tensor:
         _, h, w, _ = hidden_states.shape
+        if self._replicate(h, w):
+            return self._temporal_replicated(module, hidden_states, num_frames)   # ctx.full_hw stays None
         xs = self.to_pixel_shards(hidden_states, num_frames)
         module.ctx.full_hw = (h, w)
         try:
@@ -132,6 +153,8 @@ class FrameParallel:
 
     def temporal_conv(self, module, hidden_states: torch.Tensor, num_frames: int) -> torch.Tensor:
         _, h, w, _ = hidden_states.shape
+        if self._replicate(h, w):
+            return self._temporal_replicated(module, hidden_states, num_frames)
         xs = self.to_pixel_shards(hidden_states, num_frames)
         ys = module.forward_local(xs, num_frames, self.gather_partials)
         return self.to_frame_shards(ys, num_frames, h, w)

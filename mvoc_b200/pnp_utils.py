@@ -129,7 +129,7 @@ class _InjectingProcessor(AttnProcessor2_0):
         par = _partition(attn)
         n_frames_total = mask[0][0].shape[2]
         if self.temporal:
-            if par is not None:   # rows are this rank's pixel shard of the (fh x fw) frame
+            if par is not None and attn.ctx.full_hw is not None:   # rows are this rank's pixel shard of (fh x fw)
                 fh, fw = attn.ctx.full_hw
                 tokens = _MASKS.tokens(mask, fh, fw, soft=True, pixels=par.pixel_range(fh * fw))
             else:

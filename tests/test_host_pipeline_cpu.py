@@ -95,12 +95,13 @@ def test_host_unet_forward_vs_reference_golden(emulated_ops, case_name):
 
 
 def test_host_composite_loop_vs_oracle(emulated_ops):
-    """reduced2 (bg + 2 objects), 6 steps: fusion on step 0, feature injection on steps 0-4, attention-only after."""
+    """reduced2 (bg + 2 objects), 3 steps: fusion on step 0, feature + attention injection (the 10-step runs against
+    the reference-generated vectors below cover the attention-only steps)."""
     from oracle import pipeline as opipe
 
     wl, sched, inputs, ou = _setup("reduced2")
-    ref = opipe.composite_loop(copy.deepcopy(ou), wl, inputs, max_steps=6)
-    out = _composite(wl, sched, inputs, _product_cpu(ou, wl.unet), 6)
+    ref = opipe.composite_loop(copy.deepcopy(ou), wl, inputs, max_steps=3)
+    out = _composite(wl, sched, inputs, _product_cpu(ou, wl.unet), 3)
     err = rel_l2(out, ref)
     assert err <= TOL, f"{err:.3e}"
 
@@ -130,7 +131,22 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _fp_worker(rank, world, port, ret):
+def _fp_setup(variant):
+    """(workload, schedule, inputs, oracle UNet) of a frame-parallel scenario."""
+    if variant == "reduced2":
+        return _setup("reduced2")
+    # 4-level model on 24x24 latents: the lowest level has 3x3 = 9 pixels, which no even world size divides ->
+    # its temporal operators run replicated on all-gathered frames (FrameParallel._temporal_replicated)
+    from mvoc_b200 import synthetic
+    from mvoc_b200.scheduler import DDIMSchedule
+    from tests.golden import spec
+
+    wl = synthetic.Workload("tiny4_24", "tiny4", 4, 24, 24, 2)
+    sched = DDIMSchedule(wl.n_steps)
+    return wl, sched, synthetic.make_inputs(wl, sched.timesteps, sched.alphas_cumprod), spec.build_tiny4(seed=0)
+
+
+def _fp_worker(rank, world, port, ret, variant="reduced2", gather_max_pixels=0):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.set_num_threads(max(1, (os.cpu_count() or 2) // world))
@@ -140,11 +156,13 @@ def _fp_worker(rank, world, port, ret):
         from tests import cpu_ops_emulation as emu
 
         emu.install()
-        wl, sched, inputs, ou = _setup("reduced2")
+        FrameParallel._GATHER_MAX_PIXELS = gather_max_pixels
+        wl, sched, inputs, ou = _fp_setup(variant)
         par = FrameParallel(dist.group.WORLD, world, rank, torch.device("cpu"))
         with torch.no_grad():
             sharded = _composite(wl, sched, inputs, _product_cpu(ou, wl.unet), 2, parallel=par)
-            single = _composite(wl, sched, inputs, _product_cpu(ou, wl.unet), 2)
+            single = _composite(wl, sched, inputs, _product_cpu(ou, wl.unet), 2) if rank == 0 else torch.empty_like(sharded)
+        dist.broadcast(single, src=0)           # the single-rank reference is computed once, by rank 0
         err = rel_l2(sharded, single)
         # every rank holds the full updated latents (the prediction is all-gathered before the DDIM update)
         got = [torch.empty_like(sharded) for _ in range(world)]
@@ -159,18 +177,34 @@ def _fp_worker(rank, world, port, ret):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_host_composite_frame_parallel(world):
-    """P ranks, each running every branch on 1/P of the frames (temporal operators on pixel shards after the
-    all-to-all, GroupNorm statistics merged across shards): same latents as the single-rank loop."""
+def _run_fp(world, variant="reduced2", gather_max_pixels=0):
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_fp_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    mp.spawn(_fp_worker, args=(world, _free_port(), ret, variant, gather_max_pixels), nprocs=world, join=True)
     for r in range(world):
         status, err, same = ret.get(r)
         assert status == "ok", f"rank {r}: {err}"
         assert err <= TOL, f"rank {r}: sharded vs single {err:.3e}"
         assert same, "ranks disagree on the updated latents"
+
+
+def test_host_frame_parallel_indivisible_level_is_replicated():
+    """A level whose pixel count no rank count divides (3x3 here; config 5's 11x20 on 8 GPUs) runs its temporal
+    operators on all-gathered frames instead of pixel shards — same latents as a single rank."""
+    _run_fp(2, "tiny4_24")
+
+
+def test_host_frame_parallel_gather_threshold():
+    """MVOC_FP_GATHER_MAX_PIXELS: low-resolution levels (<= 256 pixels here: the 16x16 level of reduced2)
+    replicated by choice, the 32x32 level pixel-sharded."""
+    _run_fp(2, "reduced2", gather_max_pixels=256)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_host_composite_frame_parallel(world):
+    """P ranks, each running every branch on 1/P of the frames (temporal operators on pixel shards after the
+    all-to-all, GroupNorm statistics merged across shards): same latents as the single-rank loop."""
+    _run_fp(world)
 
 
 def test_host_staged_routing_vs_oracle(emulated_ops, monkeypatch):
@@ -205,8 +239,8 @@ def test_host_staged_routing_vs_oracle(emulated_ops, monkeypatch):
     monkeypatch.setattr(staged, "conv3x3_nhwc", conv3x3_nhwc)
     monkeypatch.setattr(staged, "linear_geglu", linear_geglu)
     wl, sched, inputs, ou = _setup("reduced2")
-    ref = opipe.composite_loop(copy.deepcopy(ou), wl, inputs, max_steps=2)
-    out = _composite(wl, sched, inputs, _product_cpu(ou, wl.unet), 2)
+    ref = opipe.composite_loop(copy.deepcopy(ou), wl, inputs, max_steps=1)
+    out = _composite(wl, sched, inputs, _product_cpu(ou, wl.unet), 1)
     assert rel_l2(out, ref) <= TOL
     assert calls["conv"] > 0 and calls["conv_res"] > 0 and calls["geglu"] > 0
 
@@ -227,8 +261,8 @@ def test_host_groupnorm_slabs_vs_oracle(emulated_ops, monkeypatch):
     monkeypatch.setattr(ops, "_groupnorm_nhwc_slab", spy)
     monkeypatch.setattr(ops, "_GN_SLAB_BYTES", 96 * 1024)      # a few frames of the reduced model per slab
     wl, sched, inputs, ou = _setup("reduced2")
-    ref = opipe.composite_loop(copy.deepcopy(ou), wl, inputs, max_steps=2)
-    out = _composite(wl, sched, inputs, _product_cpu(ou, wl.unet), 2)
+    ref = opipe.composite_loop(copy.deepcopy(ou), wl, inputs, max_steps=1)
+    out = _composite(wl, sched, inputs, _product_cpu(ou, wl.unet), 1)
     assert rel_l2(out, ref) <= TOL
     full = wl.n_branches * wl.n_frames
     assert any(n < full for n in slabs), "no call was split into slabs"
