@@ -43,6 +43,21 @@ int mvoc_conv3x3_nhwc(const void* x, const void* w_taps, const void* bias, const
 int mvoc_linear_geglu(const void* x, const void* w, const void* bias, void* out, int64_t M, int K, int F,
                       int dtype, void* stream);
 
+/*
+ * The attention entry point of mvoc_b200.h with every query row split across two softmax threads: eight softmax warps per
+ * CTA instead of four, to hide the latency of the score-row dependency chain that the ncu capture of the product
+ * kernel shows (no saturated pipe).  Same arguments, layouts and restrictions.
+ * variant 0: 3 of every 8 exp2 pairs on the FMA-pipe polynomial (as the product default); 1: all on the MUFU;
+ * 2: 4 of 8.
+ */
+int mvoc_attn_fwd_split(const void* q, const void* k, const void* v, void* o,
+                        int B, int H, int Nq, int Nk, int D,
+                        int64_t q_sb, int64_t q_sn, int64_t q_sh,
+                        int64_t k_sb, int64_t k_sn, int64_t k_sh,
+                        int64_t v_sb, int64_t v_sn, int64_t v_sh,
+                        int64_t o_sb, int64_t o_sn, int64_t o_sh,
+                        float scale, int dtype, int variant, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_int, c_int64, c_void_p
+from ctypes import c_float, c_int, c_int64, c_void_p
 from typing import Optional
 
 import torch
@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libm
 SIGNATURES = {
     "mvoc_conv3x3_nhwc": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
     "mvoc_linear_geglu": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_void_p]),
+    "mvoc_attn_fwd_split": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_int64] * 12 + [c_float, c_int, c_int, c_void_p]),
 }
 
 _lib = None
@@ -91,4 +92,23 @@ def linear_geglu(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
     rc = load().mvoc_linear_geglu(x.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(),
                                   out.data_ptr(), M, K, F, _cabi.MVOC_BF16, torch.cuda.current_stream().cuda_stream)
     _check(rc, "mvoc_linear_geglu")
+    return out
+
+
+def attention_split(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None,
+                    out: Optional[torch.Tensor] = None, variant: int = 0) -> torch.Tensor:
+    """ops.attention through the row-split kernel: q [B,Nq,H*64], k/v [B,Nk,H*64] (last dim contiguous)."""
+    for t in (q, k, v, out):
+        if t is not None and (not t.is_cuda or t.dtype != torch.bfloat16 or t.stride(-1) != 1):
+            raise ValueError("attention_split takes bf16 CUDA tensors with a contiguous last dim (no fallback)")
+    B, Nq, C = q.shape
+    if C != heads * 64 or k.shape[0] != B or v.shape != k.shape:
+        raise ValueError(f"attention_split: q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)} heads {heads}")
+    if out is None:
+        out = torch.empty((B, Nq, C), dtype=q.dtype, device=q.device)
+    st = lambda t: (t.stride(0), t.stride(1), 64)
+    rc = load().mvoc_attn_fwd_split(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, Nq, k.shape[1],
+                                    64, *st(q), *st(k), *st(v), *st(out), float(scale if scale is not None else 0.125),
+                                    _cabi.MVOC_BF16, int(variant), torch.cuda.current_stream().cuda_stream)
+    _check(rc, "mvoc_attn_fwd_split")
     return out

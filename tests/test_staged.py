@@ -83,3 +83,41 @@ def test_linear_geglu_vs_torch(M, K, F):
     out = staged.linear_geglu(x, w, b)
     torch.cuda.synchronize()
     assert _rel(out, ref) <= 5e-3
+
+
+@needs_staged_gpu
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("B,H,Nq,Nk", [(2, 5, 256, 256), (1, 1, 128, 128), (2, 2, 64, 64), (3, 10, 1024, 1024),
+                                       (2, 5, 256, 145), (1, 3, 200, 77), (1, 5, 4096, 4096), (1, 2, 880, 880),
+                                       (1, 2, 300, 200)])
+def test_attention_split_vs_oracle_and_product(B, H, Nq, Nk, variant):
+    from mvoc_b200 import ops, staged
+    from oracle import ops_ref
+
+    torch.manual_seed(B * 1000 + Nq + Nk)
+    C = H * 64
+    q, k, v = torch.randn(B, Nq, C).bfloat16(), torch.randn(B, Nk, C).bfloat16(), torch.randn(B, Nk, C).bfloat16()
+    ref = ops_ref.sdpa_ref(q.float(), k.float(), v.float(), H)
+    out = staged.attention_split(q.cuda(), k.cuda(), v.cuda(), H, variant=variant)
+    prod = ops.attention(q.cuda(), k.cuda(), v.cuda(), H)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out.cpu(), ref) <= 1e-2
+    assert _rel(out, prod) <= 5e-3
+
+
+@needs_staged_gpu
+def test_attention_split_large_scores():
+    """Rescale path: scores grow along the key axis, so the running maximum keeps moving by more than 2^8."""
+    from mvoc_b200 import staged
+    from oracle import ops_ref
+
+    torch.manual_seed(3)
+    B, H, N = 1, 2, 1024
+    q = torch.randn(B, N, H * 64).bfloat16()
+    k = (torch.randn(B, N, H * 64) * torch.linspace(0.2, 6.0, N)[None, :, None]).bfloat16()
+    v = torch.randn(B, N, H * 64).bfloat16()
+    ref = ops_ref.sdpa_ref(q.float(), k.float(), v.float(), H)
+    out = staged.attention_split(q.cuda(), k.cuda(), v.cuda(), H)
+    torch.cuda.synchronize()
+    assert _rel(out.cpu(), ref) <= 2e-2

@@ -170,8 +170,58 @@ def section_time():
     print(f"  feature_blend l0: {t:.4f} ms  {by / t / 1e6:.0f} GB/s (min bytes)")
 
 
+def section_staged():
+    """Timings of the kernels staged in libmvoc_b200_staged.so against what the product path uses today."""
+    import torch
+    import torch.nn.functional as F
+
+    from mvoc_b200 import ops, staged
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    print("== row-split attention vs product kernel (ms, TFLOP/s) ==")
+    for (B, H, N, Nk) in [(80, 5, 4096, 4096), (80, 10, 1024, 1024), (80, 20, 256, 256), (80, 5, 4096, 145)]:
+        C = H * 64
+        q = torch.randn(B, N, C, device=dev).bfloat16()
+        k = torch.randn(B, Nk, C, device=dev).bfloat16()
+        v = torch.randn(B, Nk, C, device=dev).bfloat16()
+        fl = 4.0 * B * H * N * Nk * 64
+        t = _time_cuda(lambda: ops.attention(q, k, v, H), iters=5)
+        print(f"  product      B={B} H={H} N={N} Nk={Nk}: {t:.3f} ms  {fl / t / 1e9:.1f} TF/s")
+        for variant in (0, 1, 2):
+            t = _time_cuda(lambda: staged.attention_split(q, k, v, H, variant=variant), iters=5)
+            print(f"  split v{variant}     B={B} H={H} N={N} Nk={Nk}: {t:.3f} ms  {fl / t / 1e9:.1f} TF/s")
+    print("== 3x3 conv, channels-last (ms, TFLOP/s): tcgen05 implicit GEMM vs cuDNN ==")
+    for (N, H, W, ci, co) in [(80, 64, 64, 320, 320), (80, 64, 64, 640, 320), (80, 64, 64, 960, 320),
+                              (80, 32, 32, 640, 640), (80, 32, 32, 1280, 640), (80, 16, 16, 1280, 1280),
+                              (80, 16, 16, 2560, 1280), (80, 8, 8, 1280, 1280)]:
+        x = torch.randn(N, H, W, ci, device=dev).bfloat16()
+        w = (torch.randn(co, ci, 3, 3, device=dev) * (9 * ci) ** -0.5).bfloat16()
+        b = torch.randn(co, device=dev).bfloat16()
+        wt = staged.prepare_conv_weight(w)
+        wcl = w.contiguous(memory_format=torch.channels_last)
+        fl = 2.0 * N * H * W * co * ci * 9
+        t = _time_cuda(lambda: F.conv2d(x.permute(0, 3, 1, 2), wcl, b, padding=1), iters=5)
+        print(f"  cuDNN        {N}x{H}x{W} {ci}->{co}: {t:.3f} ms  {fl / t / 1e9:.1f} TF/s")
+        for variant in (0, 1):
+            t = _time_cuda(lambda: staged.conv3x3_nhwc(x, wt, b, None, variant=variant), iters=5)
+            print(f"  tcgen05 v{variant}   {N}x{H}x{W} {ci}->{co}: {t:.3f} ms  {fl / t / 1e9:.1f} TF/s")
+    print("== GEGLU projection (ms): fused epilogue vs cuBLAS + mvoc_geglu ==")
+    for (M, K) in [(327680, 320), (81920, 640), (20480, 1280)]:
+        Fo = 4 * K
+        x = torch.randn(M, K, device=dev).bfloat16()
+        w = (torch.randn(2 * Fo, K, device=dev) * K ** -0.5).bfloat16()
+        b = torch.randn(2 * Fo, device=dev).bfloat16()
+        t0 = _time_cuda(lambda: ops.geglu(F.linear(x, w, b)), iters=5)
+        t1 = _time_cuda(lambda: staged.linear_geglu(x, w, b), iters=5)
+        fl = 2.0 * M * K * 2 * Fo
+        print(f"  M={M} K={K} F={Fo}: cuBLAS+geglu {t0:.3f} ms, fused {t1:.3f} ms ({fl / t1 / 1e9:.1f} TF/s)")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "staged":
+        section_staged()
     if what in ("attn", "all"):
         section_attn()
     if what in ("time", "all"):

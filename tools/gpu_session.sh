@@ -34,6 +34,7 @@ run 420 ncu_launches ncu --metrics gpu__time_duration.sum --clock-control none -
 MVOC_STAGED=1 run 300 staged_tests  python -m pytest tests/test_staged.py -x -q
 MVOC_GN_SLAB_MB=24 run 150 bench_gnslab24 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 MVOC_GN_SLAB_MB=48 run 150 bench_gnslab48 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+MVOC_STAGED=1 run 240 staged_times  python tools/gpu_diag.py staged
 if grep -q "passed" "$OUT/${TAG}_staged_tests.log" && ! grep -q "failed" "$OUT/${TAG}_staged_tests.log"; then
     MVOC_STAGED=1 run 420 staged_pytest_gpu python -m pytest tests -m gpu -x -q
     MVOC_STAGED=1 run 150 bench_staged python bench.py --steps 10 --warmup 3 --no-cpu-baseline
