@@ -373,6 +373,9 @@ def run_mvoc(args):
             "timed_steps_start_at": 0,
             "cuda_graphs": bool(pipe.use_cuda_graphs),
             "eager_ms_per_step": ms_eager_total / K,
+            # experiment switches (all off for the product numbers; a line with any of them set is an A/B line)
+            "switches": {k: os.environ[k] for k in ("MVOC_STAGED", "MVOC_GN_SLAB_MB", "MVOC_FP_GATHER_MAX_PIXELS")
+                         if os.environ.get(k)},
         },
         "roofline": roof,
         "cpu_baseline": cpu,
