@@ -41,6 +41,9 @@ def load() -> ctypes.CDLL:
 def _check(rc: int, what: str) -> None:
     if rc != 0:
         raise RuntimeError(f"{what} failed ({rc}): {load().mvoc_last_error().decode()}")
+    from . import ops
+
+    ops._count()          # bench.py's gpu_launches counts these launches too
 
 
 def _need(*ts) -> None:
