@@ -316,3 +316,23 @@ def test_host_inversion_loop_vs_reference_golden(emulated_ops):
     assert sorted(saved) == [1, 3, 5]
     for t in saved:
         assert rel_l2(saved[t], gold["latents_at_t"][t]) <= TOL
+
+
+@pytest.mark.skipif(os.environ.get("MVOC_LONG_TESTS") != "1", reason="1.4 B-parameter model twice in fp32: ~12 GB, minutes")
+def test_host_full_architecture_forward_vs_oracle(emulated_ops):
+    """The FULL i2vgen-xl architecture (320/640/1280/1280, 5/10/20 heads — the benchmark's model) through the
+    product host layer against the oracle, one composite step on 2 frames x 16x16 latents, every hook firing."""
+    from mvoc_b200 import synthetic
+    from mvoc_b200.scheduler import DDIMSchedule
+    from oracle import pipeline as opipe
+
+    wl = synthetic.Workload("full_tiny", "full", 2, 16, 16, 2)
+    sched = DDIMSchedule(wl.n_steps)
+    inputs = synthetic.make_inputs(wl, sched.timesteps, sched.alphas_cumprod)
+    ou = opipe.build_unet("full", seed=0)
+    with torch.no_grad():
+        ref = opipe.composite_loop(ou, wl, inputs, max_steps=1)
+        pu = _product_cpu(ou, "full")
+        del ou
+        out = _composite(wl, sched, inputs, pu, 1)
+    assert rel_l2(out, ref) <= TOL
