@@ -141,7 +141,8 @@ def _fp_setup(variant):
     from mvoc_b200.scheduler import DDIMSchedule
     from tests.golden import spec
 
-    wl = synthetic.Workload("tiny4_24", "tiny4", 4, 24, 24, 2)
+    wl = (synthetic.Workload("tiny4_24", "tiny4", 4, 24, 24, 2) if variant == "tiny4_24"
+          else synthetic.Workload("tiny4_t8", "tiny4", 8, 32, 32, 2))       # 8 ranks: one frame each, h == world at 8x8
     sched = DDIMSchedule(wl.n_steps)
     return wl, sched, synthetic.make_inputs(wl, sched.timesteps, sched.alphas_cumprod), spec.build_tiny4(seed=0)
 
@@ -336,3 +337,10 @@ def test_host_full_architecture_forward_vs_oracle(emulated_ops):
         del ou
         out = _composite(wl, sched, inputs, pu, 1)
     assert rel_l2(out, ref) <= TOL
+
+
+@pytest.mark.skipif(os.environ.get("MVOC_LONG_TESTS") != "1", reason="8 processes; about a minute")
+def test_host_composite_frame_parallel_world8():
+    """Eight ranks with one frame each on the 4-level model (the 8x8 level has h == world_size, the layout that
+    once produced a non-contiguous relayout on the 8-GPU box)."""
+    _run_fp(8, "tiny4_t8")
