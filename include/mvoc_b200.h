@@ -7,6 +7,11 @@
  * negative error code and the text is available from mvoc_last_error().
  * sm_100a only.
  *
+ * Threading / devices: the library is built for one process per GPU (the deployment model of this repo).
+ * Calls may come from any host thread but not concurrently; launches go to the current device, and the
+ * one-time per-kernel attributes (dynamic shared-memory size) are set for the device of the first call, so
+ * a process must stay on one device.  mvoc_last_error() is thread-local.
+ *
  * Each function cites the reference interface it replaces (paths relative to
  * the SobeyMIL/MVOC tree).  The reference is Python on diffusers; the
  * binding a maintainer would add is a ctypes stub — see INTEGRATION.md.
