@@ -121,3 +121,63 @@ def test_attention_split_large_scores():
     out = staged.attention_split(q.cuda(), k.cuda(), v.cuda(), H)
     torch.cuda.synchronize()
     assert _rel(out.cpu(), ref) <= 2e-2
+
+
+def _choose_box(N, H, W):
+    """Python mirror of gemm::choose_box (gemm_tc.cu): powers of two (bn, bh, bw), product 128, least padding."""
+    best = None
+    w = 128
+    while w >= 1:
+        h = 128 // w
+        while h >= 1:
+            n = 128 // (w * h)
+            padded = -(-W // w) * w * (-(-H // h) * h) * (-(-N // n) * n)
+            if best is None or padded < best[0]:
+                best = (padded, n, h, w)
+            h //= 2
+        w //= 2
+    return best[1:]
+
+
+@pytest.mark.parametrize("N,H,W,ci,co", [(2, 11, 20, 64, 64), (3, 16, 16, 128, 64), (5, 8, 8, 64, 128)])
+def test_conv_tiling_model(N, H, W, ci, co):
+    """CPU model of the staged conv kernel's data movement (not of the hardware): per CTA, nine shifted, zero-filled
+    boxes {64 ch, bw, bh, bn} of the NHWC activation times the tap-major weights, rows = (n, h, w) of the box,
+    stores masked to real pixels — must equal conv2d.  Guards the tile / tap / layout arithmetic of gemm_tc.cu."""
+    from mvoc_b200 import staged
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(N, H, W, ci, generator=g)
+    w = torch.randn(co, ci, 3, 3, generator=g)
+    wt = staged.prepare_conv_weight(w)                                   # [9, co, ci]
+    bn, bh, bw = _choose_box(N, H, W)
+    assert bn * bh * bw == 128
+    out = torch.full((N, H, W, co), float("nan"))
+
+    def box(n0, h0, w0, c0):                                             # TMA tile load with zero OOB fill
+        t = torch.zeros(bn, bh, bw, 64)
+        for a in range(bn):
+            for b in range(bh):
+                for c in range(bw):
+                    n, hh, ww = n0 + a, h0 + b, w0 + c
+                    if 0 <= n < N and 0 <= hh < H and 0 <= ww < W:
+                        t[a, b, c] = x[n, hh, ww, c0:c0 + 64]
+        return t.reshape(128, 64)
+
+    for tn in range(-(-N // bn)):
+        for th in range(-(-H // bh)):
+            for tw in range(-(-W // bw)):
+                acc = torch.zeros(128, co)
+                for kc in range(ci // 64):
+                    for tap in range(9):
+                        kh, kw = divmod(tap, 3)
+                        a = box(tn * bn, th * bh + kh - 1, tw * bw + kw - 1, kc * 64)
+                        acc += a @ wt[tap, :, kc * 64:(kc + 1) * 64].t()
+                for row in range(128):
+                    iw, ih, i_n = row % bw, (row // bw) % bh, row // (bw * bh)
+                    n, hh, ww = tn * bn + i_n, th * bh + ih, tw * bw + iw
+                    if n < N and hh < H and ww < W:
+                        out[n, hh, ww] = acc[row]
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1)
+    assert not torch.isnan(out).any()
+    assert torch.allclose(out, ref, atol=1e-3, rtol=1e-4)
