@@ -3,7 +3,7 @@
 # timeout so that a hang costs minutes, not the budget (round 1 lost ~98 GPU-minutes to two multi-rank runs
 # that hung at exit under a 600 s limit).  Usage, from the build container:
 #
-#   gpurun --timeout 2400 -- 'bash tools/gpu_session.sh r02'
+#   gpurun --timeout 3000 -- 'bash tools/gpu_session.sh r02'   # ~45 GPU-minutes worst case
 #
 # Output: gpurun_out/<tag>_*  (copy what should be judged into profiles/).
 set -u
@@ -27,9 +27,10 @@ run 120 kernel_times python tools/gpu_diag.py time
 run 240 ncu_attn     ncu --set full --clock-control none --import-source on -k regex:attn_fwd_kernel -s 2 -c 1 \
                          -f -o "$OUT/${TAG}_attn_l0" python tools/attn_profile.py
 # launch list of ONE timed step (NVTX range pushed by bench.py), eager launches so every kernel is listed
-run 420 ncu_launches ncu --metrics gpu__time_duration.sum --clock-control none --nvtx \
+# (round 1: 150 s covered 45 % of one step under ncu; a full step needs ~6 minutes)
+run 780 ncu_launches ncu --metrics gpu__time_duration.sum --clock-control none --nvtx \
                          --nvtx-include "mvoc_timed_region/" --csv --log-file "$OUT/${TAG}_launches_timed_step.csv" \
-                         python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graphs
+                         python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graphs
 # ---- options that were staged without hardware: numerics first, then A/B bench lines (K=10 each)
 MVOC_STAGED=1 run 300 staged_tests  python -m pytest tests/test_staged.py -x -q
 MVOC_GN_SLAB_MB=24 run 150 bench_gnslab24 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
