@@ -32,6 +32,9 @@ run 780 ncu_launches ncu --metrics gpu__time_duration.sum --clock-control none -
                          --nvtx-include "mvoc_timed_region/" --csv --log-file "$OUT/${TAG}_launches_timed_step.csv" \
                          python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graphs
 # ---- options that were staged without hardware: numerics first, then A/B bench lines (K=10 each)
+for sec in conv geglu attn time; do   # standalone binary, one section per process (a trap only loses its own section)
+    run 150 staged_check_$sec tools/staged_check $sec
+done
 MVOC_STAGED=1 run 300 staged_tests  python -m pytest tests/test_staged.py -x -q
 MVOC_GN_SLAB_MB=24 run 150 bench_gnslab24 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
 MVOC_GN_SLAB_MB=48 run 150 bench_gnslab48 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
