@@ -302,6 +302,12 @@ def test_host_composition_loop_vs_reference_golden(emulated_ops, case):
             assert rel_l2(rec[i], ref) <= TOL, f"{case} step {i}: {rel_l2(rec[i], ref):.3e}"
             checked += 1
     assert checked >= 5
+    # the same as PSNR of decoded frames, one oracle-side decoder for both latents
+    from oracle import vae
+
+    dec = vae.build_decoder()
+    db = vae.psnr(vae.decode_latents(dec, rec[9]), vae.decode_latents(dec, gold["latents_after_step"][case][9]))
+    assert db >= 100.0, db
 
 
 def test_host_inversion_loop_vs_reference_golden(emulated_ops):

@@ -109,3 +109,23 @@ def test_oracle_reproduces_reference_inversion_loop():
             assert err <= 1e-5, f"t={t}: {err:.3e}"
             checked += 1
     assert checked >= 3
+
+
+def test_vae_decoder_restatement_structure():
+    """oracle/vae.py: the full-width decoder has the parameter count of the published SD / i2vgen-xl VAE decoder
+    (49 490 179 + the 4->4 post_quant_conv), decode_latents keeps the reference's layout (pipeline :771-791)."""
+    from oracle import vae
+
+    full = vae.build_decoder(narrow=False)
+    assert sum(p.numel() for p in full.parameters()) == 49_490_179 + 20
+    dec = vae.build_decoder()
+    lat = torch.randn(2, 4, 3, 8, 8, generator=torch.Generator().manual_seed(0)) * vae.SCALING_FACTOR
+    video = vae.decode_latents(dec, lat, decode_chunk_size=2)
+    assert video.shape == (2, 3, 3, 64, 64) and video.dtype == torch.float32
+    # frame f of video b depends only on latent frame f of video b
+    lat2 = lat.clone()
+    lat2[1, :, 2] += 0.1
+    v2 = vae.decode_latents(dec, lat2)
+    assert torch.equal(v2[0], video[0]) and torch.equal(v2[1, :, :2], video[1, :, :2])
+    assert not torch.equal(v2[1, :, 2], video[1, :, 2])
+    assert vae.psnr(video, video) == float("inf") and vae.psnr(v2, video) < 80

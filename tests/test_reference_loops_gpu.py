@@ -54,6 +54,15 @@ def test_composition_loop_vs_reference_golden(cuda_device, case):
     errs = {i: rel_l2(rec[i], ref) for i, ref in gold["latents_after_step"][case].items() if i in rec}
     print(f"[reference loop, {case}] rel L2 per step {errs}")
     assert len(errs) >= 5 and max(errs.values()) <= 2e-2, errs
+    # the same comparison as PSNR of frames decoded from both latents by ONE oracle-side decoder
+    # (random-init AutoencoderKL decoder restatement, oracle/vae.py).  bf16 CPU run of these steps: 67 dB.
+    from oracle import vae
+
+    dec = vae.build_decoder()
+    last = max(errs)
+    db = vae.psnr(vae.decode_latents(dec, rec[last]), vae.decode_latents(dec, gold["latents_after_step"][case][last]))
+    print(f"[reference loop, {case}] PSNR of decoded frames after step {last}: {db:.1f} dB")
+    assert db >= 45.0, db
 
 
 def test_inversion_loop_vs_reference_golden(cuda_device):
