@@ -26,7 +26,9 @@ extern "C" {
  * torch weight [Cout, Cin, 3, 3].permute(2, 3, 0, 1).reshape(9, Cout, Cin).
  * bias: [Cout] bf16 or NULL.   residual: [N, H, W, Cout] bf16 added to the result, or NULL.
  * out: [N, H, W, Cout] bf16.   Cin % 64 == 0, Cout % 64 == 0.
- * variant 0: widest output-channel tile dividing Cout (320, 160, 128, 64); 1: never the 320-column tile.
+ * variant 0: widest output-channel tile dividing Cout (320, 160, 128, 64); 1: never the 320-column tile;
+ * 2 (Cout % 320 == 0): 320-column tiles in clusters of two CTAs on neighbouring pixel tiles that share the
+ *    weight tile — each CTA loads one half of it and TMA-multicasts it to both (half the L2 traffic of the weights).
  */
 int mvoc_conv3x3_nhwc(const void* x, const void* w_taps, const void* bias, const void* residual, void* out,
                       int N, int H, int W, int Cin, int Cout, int dtype, int variant, void* stream);

@@ -64,9 +64,38 @@ struct Params {
     int gate_row_offset;           // geglu: row of Wt where the gate half starts (F); conv: unused
 };
 
-template <typename C, int kEpi>
-__global__ void __launch_bounds__(THREADS, C::kCtas)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const Params prm) {
+// ---- thread-block-cluster pieces of the kCluster variant (pairs of CTAs that share the weight tile) ----------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA tile load written to the same shared-memory offset of every CTA in cta_mask; each destination CTA's mbarrier
+// (same offset) receives the complete_tx of the bytes it got.
+__device__ __forceinline__ void tma_load_4d_multicast(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1,
+                                                      int c2, int c3, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(dst),
+        "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+        : "memory");
+}
+// tcgen05.commit whose mbarrier arrive is delivered to the barrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::
+                     "r"(bar), "h"(cta_mask)
+                 : "memory");
+}
+
+// kCluster: the grid is launched in clusters of two CTAs that work on two neighbouring pixel tiles and the SAME
+// column tile.  Each CTA loads its own activation tile, but only ONE of the two weight pieces, multicast into both
+// CTAs: the L2 -> SM traffic of the weights, the larger operand, halves.
+template <typename C, int kEpi, bool kCluster>
+__device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tm_x, const CUtensorMap& tm_w, const Params& prm) {
+    static_assert(!kCluster || C::kPieces == 2, "the cluster variant splits the two weight pieces between two CTAs");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t sbase = smem_u32(smem_raw);
     if ((sbase & 1023u) != 0u) {
@@ -79,8 +108,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // column tile fastest: CTAs that share an activation tile are launched next to each other (L2 reuse)
-    const int n_tile = blockIdx.x % prm.n_tiles;
-    int m_tile = blockIdx.x / prm.n_tiles;
+    const uint32_t crank = kCluster ? cluster_ctarank() : 0u;
+    int n_tile, m_tile;
+    if (kCluster) {   // CTA pair p: column tile p % n_tiles, pixel tiles 2 * (p / n_tiles) + {0, 1}
+        const int pair = blockIdx.x >> 1;
+        n_tile = pair % prm.n_tiles;
+        m_tile = (pair / prm.n_tiles) * 2 + (int)crank;   // may be one past the last tile: all loads OOB, no stores
+    } else {
+        n_tile = blockIdx.x % prm.n_tiles;
+        m_tile = blockIdx.x / prm.n_tiles;
+    }
     const int tw = m_tile % prm.tiles_w;
     m_tile /= prm.tiles_w;
     const int th = m_tile % prm.tiles_h;
@@ -96,7 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         ptx::prefetch_tensormap(&tm_w);
         for (int s = 0; s < C::kStages; ++s) {
             ptx::mbar_init(b_full + 8 * s, 1);
-            ptx::mbar_init(b_empty + 8 * s, 1);
+            ptx::mbar_init(b_empty + 8 * s, kCluster ? 2 : 1);   // cluster: both CTAs' MMAs read what I multicast
         }
         ptx::mbar_init(b_acc, 1);
         ptx::fence_mbar_init();
@@ -108,6 +145,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
+    if (kCluster) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + C::tmem_ptr_off);
 
     if (warp == 4) {
@@ -127,7 +165,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                     int wrow;
                     if (kEpi == EPI_GEGLU) wrow = out_col0 + p * prm.gate_row_offset;   // piece 0 value, 1 gate
                     else wrow = out_col0 + p * C::NP;
-                    ptx::tma_load_4d(sB + p * (C::NP * KC * 2), &tm_w, b_full + 8 * s, kc * KC, wrow, tap, 0);
+                    if (!kCluster)
+                        ptx::tma_load_4d(sB + p * (C::NP * KC * 2), &tm_w, b_full + 8 * s, kc * KC, wrow, tap, 0);
+                    else if (p == (int)crank)   // my piece goes to both CTAs; the peer sends me the other one
+                        tma_load_4d_multicast(sB + p * (C::NP * KC * 2), &tm_w, b_full + 8 * s, kc * KC, wrow, tap, 0,
+                                              (uint16_t)0x3);
                 }
             }
             __syncwarp();
@@ -151,7 +193,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                         ptx::mma_ss(tmem + p * C::NP, a0 + (uint64_t)(ks * 2), b0 + (uint64_t)(ks * 2), IDESC,
                                     (c > 0 || ks > 0) ? 1u : 0u);
                 }
-                ptx::tc_commit(b_empty + 8 * s);                 // stage reusable once these MMAs have read it
+                if (kCluster) tc_commit_multicast(b_empty + 8 * s, (uint16_t)0x3);   // frees the stage in BOTH producers
+                else ptx::tc_commit(b_empty + 8 * s);            // stage reusable once these MMAs have read it
                 if (c == n_chunks - 1) ptx::tc_commit(b_acc);    // accumulators complete
             }
             __syncwarp();
@@ -221,6 +264,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem, C::tmem_cols);
     }
+    if (kCluster) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it / arrive on it
+}
+
+template <typename C, int kEpi>
+__global__ void __launch_bounds__(THREADS, C::kCtas)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const Params prm) {
+    gemm_tc_body<C, kEpi, false>(tm_x, tm_w, prm);
+}
+
+template <typename C, int kEpi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, C::kCtas)
+gemm_tc_cluster_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                       const Params prm) {
+    gemm_tc_body<C, kEpi, true>(tm_x, tm_w, prm);
 }
 
 // ------------------------------------------------------------------ host ---
@@ -285,6 +342,23 @@ static int launch(const CUtensorMap& mx, const CUtensorMap& mw, const Params& pr
     return check_launch(what);
 }
 
+// clusters of two CTAs along the pixel axis: m_tiles is rounded up to an even number
+template <typename C, int kEpi>
+static int launch_cluster(const CUtensorMap& mx, const CUtensorMap& mw, const Params& prm, int64_t m_tiles,
+                          cudaStream_t s, const char* what) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_cluster_kernel<C, kEpi>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, C::alloc);
+        MVOC_REQUIRE(e == cudaSuccess, MVOC_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int64_t ctas = ((m_tiles + 1) / 2) * 2 * prm.n_tiles;
+    MVOC_REQUIRE(ctas > 0 && ctas <= 0x7fffffffLL, MVOC_ERR_UNSUPPORTED, "%s: %lld CTAs", what, (long long)ctas);
+    gemm_tc_cluster_kernel<C, kEpi><<<(unsigned)ctas, THREADS, C::alloc, s>>>(mx, mw, prm);
+    return check_launch(what);
+}
+
 // tile configurations: accumulator columns, MMA pieces, pipeline stages, CTAs per SM
 using Cfg320 = Cfg<320, 2, 4, 1>;   // 128 x 320: one activation tile feeds 320 channels (least L2 traffic per FLOP)
 using Cfg160 = Cfg<160, 1, 3, 2>;   // 128 x 160, two CTAs per SM (the other CTA's epilogue hides behind MMAs)
@@ -305,7 +379,9 @@ extern "C" int mvoc_conv3x3_nhwc(const void* x, const void* w_taps, const void* 
     MVOC_REQUIRE(N > 0 && H > 0 && W > 0, MVOC_ERR_INVALID_ARG, "%s: empty activation N=%d H=%d W=%d", what, N, H, W);
     MVOC_REQUIRE(Cin > 0 && Cin % 64 == 0 && Cout > 0 && Cout % 64 == 0, MVOC_ERR_UNSUPPORTED,
                  "%s: Cin=%d / Cout=%d must be multiples of 64", what, Cin, Cout);
-    MVOC_REQUIRE(variant >= 0 && variant <= 1, MVOC_ERR_INVALID_ARG, "%s: unknown variant %d", what, variant);
+    MVOC_REQUIRE(variant >= 0 && variant <= 2, MVOC_ERR_INVALID_ARG, "%s: unknown variant %d", what, variant);
+    MVOC_REQUIRE(variant != 2 || Cout % 320 == 0, MVOC_ERR_UNSUPPORTED,
+                 "%s: variant 2 (CTA pairs sharing the weight tile) needs Cout %% 320 == 0, got %d", what, Cout);
     MVOC_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)w_taps % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
                      ((uintptr_t)bias % 16 == 0) && ((uintptr_t)residual % 16 == 0),
                  MVOC_ERR_INVALID_ARG, "%s: pointers must be 16-byte aligned", what);
@@ -323,7 +399,7 @@ extern "C" int mvoc_conv3x3_nhwc(const void* x, const void* w_taps, const void* 
     prm.out_ld = Cout;
     prm.gate_row_offset = 0;
     // variant 0: widest tile that divides Cout; variant 1: never the single-CTA 320-column tile
-    int BN = Cout % 320 == 0 && variant == 0 ? 320 : Cout % 160 == 0 ? 160 : Cout % 128 == 0 ? 128 : 64;
+    int BN = Cout % 320 == 0 && variant != 1 ? 320 : Cout % 160 == 0 ? 160 : Cout % 128 == 0 ? 128 : 64;
     prm.n_tiles = Cout / BN;
     const int NP = BN == 320 ? 160 : BN;
 
@@ -343,6 +419,7 @@ extern "C" int mvoc_conv3x3_nhwc(const void* x, const void* w_taps, const void* 
     }
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t ctas = m_tiles * prm.n_tiles;
+    if (variant == 2) return gemm::launch_cluster<gemm::Cfg320, gemm::EPI_BIAS>(mx, mw, prm, m_tiles, s, what);
     switch (BN) {
         case 320: return gemm::launch<gemm::Cfg320, gemm::EPI_BIAS>(mx, mw, prm, ctas, s, what);
         case 160: return gemm::launch<gemm::Cfg160, gemm::EPI_BIAS>(mx, mw, prm, ctas, s, what);

@@ -49,13 +49,18 @@ def _rel(a, b):
     (4, 32, 32, 128, 128),    # 4x32 box, BN 128
     (16, 8, 8, 128, 160),     # 2 frames per box, BN 160
     (3, 16, 16, 64, 320),     # BN 320 (two MMA pieces) and BN 160 via variant 1; N not a multiple of the box
+    (5, 16, 16, 128, 640),    # two column tiles; 10 pixel tiles -> 5 CTA pairs per column tile (variant 2)
+    (3, 8, 8, 64, 320),       # 2 frames per box: 2 pixel tiles = one CTA pair (variant 2)
+    (5, 8, 8, 64, 320),       # 3 pixel tiles: the CTA-pair variant pads with one all-out-of-range tile
     (2, 11, 20, 64, 64),      # ragged H, W (config 5's lowest level): zero-filled pixels, masked stores
 ])
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_conv3x3_vs_torch(shape, variant):
     from mvoc_b200 import staged
 
     N, H, W, ci, co = shape
+    if variant == 2 and co % 320:
+        pytest.skip("the CTA-pair variant needs Cout % 320 == 0")
     g = torch.Generator(device="cuda").manual_seed(0)
     x = torch.randn(N, H, W, ci, device="cuda", generator=g).bfloat16()
     w = (torch.randn(co, ci, 3, 3, device="cuda", generator=g) * (9 * ci) ** -0.5).bfloat16()

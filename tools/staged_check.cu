@@ -1,7 +1,7 @@
 // Standalone checker for the kernels staged in libmvoc_b200_staged.so (no Python, no torch: starts in
 // milliseconds on a fresh GPU box).  Every case compares against a naive fp32 GPU reference written here.
 //
-//   make -C tools staged_check        (or the nvcc line in tools/Makefile)
+//   built by __graft_entry__.build() next to the libraries it links (tools/staged_check, rpath = ../mvoc_b200/lib)
 //   tools/staged_check conv | geglu | attn | time        one section per process: a trap in one kernel must not
 //                                                         take the other sections down with it
 #include <cuda_bf16.h>
@@ -163,12 +163,14 @@ static int report(const char* what, int rc, double err, double bar) {
 // ------------------------------------------------------------------ sections
 static int section_conv() {
     const int cases[][5] = {{2, 64, 64, 64, 64},   {4, 32, 32, 128, 128}, {16, 8, 8, 128, 160},
-                            {3, 16, 16, 64, 320},  {2, 11, 20, 64, 64},   {5, 64, 64, 320, 320}};
+                            {3, 16, 16, 64, 320},  {2, 11, 20, 64, 64},   {5, 64, 64, 320, 320},
+                            {5, 8, 8, 64, 320},    {5, 16, 16, 128, 640}};
     int bad = 0;
     for (auto& c : cases)
-        for (int variant = 0; variant < 2; ++variant)
+        for (int variant = 0; variant < 3; ++variant)
             for (int with_res = 0; with_res < 2; ++with_res) {
                 const int N = c[0], H = c[1], W = c[2], ci = c[3], co = c[4];
+                if (variant == 2 && co % 320 != 0) continue;   // CTA-pair variant: 320-column tiles only
                 const size_t px = (size_t)N * H * W;
                 bf16* x = dev_random(px * ci, 1.0f);
                 bf16* wt = dev_random((size_t)9 * co * ci, 1.0f / sqrtf(9.0f * ci));
@@ -278,7 +280,8 @@ static int section_time() {
         bf16 *x = dev_random(px * ci, 1.0f), *wt = dev_random((size_t)9 * co * ci, 0.02f), *bias = dev_random(co, 1.0f),
              *y = dev_alloc<bf16>(px * co);
         const double fl = 2.0 * px * co * (double)ci * 9;
-        for (int variant = 0; variant < 2; ++variant) {
+        for (int variant = 0; variant < 3; ++variant) {
+            if (variant == 2 && co % 320 != 0) continue;
             const float t = time_ms([&] { mvoc_conv3x3_nhwc(x, wt, bias, nullptr, y, N, Hh, W, ci, co, MVOC_BF16, variant, nullptr); }, 5);
             printf("conv %dx%dx%d %4d->%4d v%d : %.3f ms  %.0f TF/s\n", N, Hh, W, ci, co, variant, t, fl / t / 1e9);
         }
