@@ -195,13 +195,15 @@ def test_host_frame_parallel_indivisible_level_is_replicated():
     _run_fp(2, "tiny4_24")
 
 
+@pytest.mark.skipif(os.environ.get("MVOC_LONG_TESTS") != "1", reason="optional switch; ~25 s")
 def test_host_frame_parallel_gather_threshold():
     """MVOC_FP_GATHER_MAX_PIXELS: low-resolution levels (<= 256 pixels here: the 16x16 level of reduced2)
     replicated by choice, the 32x32 level pixel-sharded."""
     _run_fp(2, "reduced2", gather_max_pixels=256)
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, pytest.param(4, marks=pytest.mark.skipif(
+    os.environ.get("MVOC_LONG_TESTS") != "1", reason="4 processes; ~30 s (world 2 runs by default, 8 is long too)"))])
 def test_host_composite_frame_parallel(world):
     """P ranks, each running every branch on 1/P of the frames (temporal operators on pixel shards after the
     all-to-all, GroupNorm statistics merged across shards): same latents as the single-rank loop."""
