@@ -341,7 +341,13 @@ def run_mvoc(args):
             "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/r01_ncu_attn_l0_v3_summary.txt",
         }
     gn_keys = [k for k in summ if k[0] == "groupnorm"]
+    gemm_keys = [k for k in summ if k[0] == "gemm"]
+    gemm_ms = sum(summ[k][1] for k in gemm_keys)
     extra = {
+        "gemm_tflops_all": (sum(summ[k][2] for k in gemm_keys) / (gemm_ms / 1e3) / 1e12) if gemm_ms else None,
+        "gemm_share_of_step": gemm_ms / ms_total if gemm_keys else None,
+        "conv3x3_tflops": (lambda ks: (sum(summ[k][2] for k in ks) / (sum(summ[k][1] for k in ks) / 1e3) / 1e12)
+                           if ks else None)([k for k in gemm_keys if k[1] == "conv3x3"]),
         "attn_tflops_all": (attn_flops / (attn_ms / 1e3) / 1e12) if attn_ms else None,
         "attn_share_of_step": attn_ms / ms_total if ms_total else None,
         "temporal_attn_gbs": (sum(summ[k][2] for k in tattn_keys) / (sum(summ[k][1] for k in tattn_keys) / 1e3) / 1e9)
@@ -374,7 +380,7 @@ def run_mvoc(args):
             "cuda_graphs": bool(pipe.use_cuda_graphs),
             "eager_ms_per_step": ms_eager_total / K,
             # experiment switches (all off for the product numbers; a line with any of them set is an A/B line)
-            "switches": {k: os.environ[k] for k in ("MVOC_STAGED", "MVOC_GN_SLAB_MB", "MVOC_FP_GATHER_MAX_PIXELS")
+            "switches": {k: os.environ[k] for k in ("MVOC_DENSE", "MVOC_GEMM_VARIANT", "MVOC_GN_SLAB_MB", "MVOC_FP_GATHER_MAX_PIXELS")
                          if os.environ.get(k)},
         },
         "roofline": roof,

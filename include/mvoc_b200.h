@@ -208,6 +208,54 @@ int mvoc_layernorm(const void* x, void* y, const void* gamma, const void* beta, 
 int mvoc_geglu(const void* x, void* y, int64_t M, int F, int dtype, void* stream);
 
 /*
+ * ---- dense work on tcgen05 tensor cores (csrc/gemm_tc.cu) ------------------------------------------------
+ * One persistent implicit-GEMM kernel: 128-row activation tiles are TMA boxes of the channels-last tensor
+ * (shifted per filter tap, zero-filled outside = the padding), weights are K-major [tap, Cout, Cin], fp32
+ * accumulation in TMEM (two buffers), epilogue fuses bias / residual / GEGLU and leaves through TMA stores.
+ * bf16 or fp16 storage (MVOC_BF16 / MVOC_F16); channel counts multiples of 64; pointers 16-byte aligned.
+ * variant: bit 0 = run as CTA pairs (tcgen05 cta_group::2, 256-row tiles); bits 8..16 = tile width override
+ * (256 / 192 / 160 / 128 / 64; 0 = widest that divides Cout).  Outputs may not alias inputs.
+ */
+
+/*
+ * 3x3 convolution, stride 1, padding 1, channels-last: out[N,H,W,Cout] = conv(x[N,H,W,Cin], w) + bias
+ * (+ x2[N,H,W,Cin2] . w2[Cout,Cin2], the resnet's 1x1 shortcut conv accumulated in the same tile)
+ * (+ residual[N,H,W,Cout]).  w_taps: [9, Cout, Cin] (tap = kh*3+kw), i.e. conv.weight.permute(2,3,0,1).
+ * Replaces conv1 / conv2 / conv_shortcut + the skip add of the resnet closure, i2vgen-xl/pnp_utils.py:939,
+ * :968, :1011-1018, and the same calls inside diffusers' stock ResnetBlock2D / Upsample2D.
+ */
+int mvoc_conv3x3_nhwc(const void* x, const void* w_taps, const void* bias, const void* residual,
+                      const void* x2, const void* w2, int Cin2, void* out,
+                      int N, int H, int W, int Cin, int Cout, int dtype, int variant, void* stream);
+
+/*
+ * Temporal convolution Conv3d(kernel (3,1,1), padding (1,0,0)) on frame-major channels-last rows:
+ * x [B, T, S, Cin] -> out [B, T, S, Cout] (+ bias, + residual), w_taps [3, Cout, Cin] (tap = frame offset + 1).
+ * Replaces the Conv3d of TemporalConvLayer.conv1..4 and the identity add, i2vgen-xl/pnp_utils.py:1048-1053;
+ * the [(b t) c h w] <-> [b c t h w] permutes of :1044-1046, :1055-1057 are never materialised.
+ */
+int mvoc_temporal_conv3(const void* x, const void* w_taps, const void* bias, const void* residual, void* out,
+                        int B, int T, int64_t S, int Cin, int Cout, int dtype, int variant, void* stream);
+
+/*
+ * Linear / 1x1 conv: out[M, N] = x[M, K] . w[N, K]^T (+ bias[N]) (+ residual[M, N]); row strides ldx / ldr /
+ * ldo in elements (multiples of 8).  Replaces to_q / to_k / to_v / to_out[0] (i2vgen-xl/pnp_utils.py:604-612,
+ * :692 — bias + the block's residual add :283/:315 in the epilogue), proj_in / proj_out (:191, :206, :432,
+ * :503-508), ff.net[2] (:335-342) and the K/V projections of the cross-attention.
+ */
+int mvoc_linear(const void* x, const void* w, const void* bias, const void* residual, void* out,
+                int64_t M, int K, int N, int64_t ldx, int64_t ldr, int64_t ldo,
+                int dtype, int variant, void* stream);
+
+/*
+ * GEGLU projection with the gate in the epilogue: out[M, F] = (x . w[:F]^T + b[:F]) * gelu(x . w[F:]^T + b[F:])
+ * (exact erf GELU); w [2F, K], bias [2F].  The [M, 2F] intermediate of diffusers' GEGLU
+ * (i2vgen-xl/pnp_utils.py:335: proj, chunk, gelu, multiply) never reaches HBM.  F % 64 == 0.
+ */
+int mvoc_linear_geglu(const void* x, const void* w, const void* bias, void* out, int64_t M, int K, int F,
+                      int dtype, int variant, void* stream);
+
+/*
  * Latent compositing ("noise fusion") fused with the UNet input concat.
  * Replaces pipelines/pipeline_i2vgen_xl.py:1644-1663 and the torch.cat at
  * :1675-1677.

@@ -72,6 +72,13 @@ SIGNATURES = {
         c_int,
         [c_void_p] * 4 + [c_int64, c_int, c_int64, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p],
     ),
+    "mvoc_conv3x3_nhwc": (
+        c_int, [c_void_p] * 6 + [c_int, c_void_p] + [c_int] * 5 + [c_int, c_int, c_void_p]),
+    "mvoc_temporal_conv3": (
+        c_int, [c_void_p] * 5 + [c_int, c_int, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
+    "mvoc_linear": (
+        c_int, [c_void_p] * 5 + [c_int64, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "mvoc_linear_geglu": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_int, c_void_p]),
     "mvoc_latent_composite": (
         c_int,
         [c_void_p] * 5 + [c_int, c_int64, c_int64, c_float, c_int, c_int, c_int, c_int, c_void_p],

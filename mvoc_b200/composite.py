@@ -12,10 +12,12 @@ masks (utils.mask_preprocess) and runs the 50-step composition loop
 
 Out of scope here: CLIP / VAE.  The tensors those stages produce are read from
 `--conditioning file.pt` (a dict with prompt_embeds [n+3,77,1024], image_embeddings [n+3,T,1024],
-image_latents_first / image_latents [n+3,4,T,h,w]) when given; otherwise — and when the latent / mask paths
-of an entry do not exist — seeded synthetic tensors of the right shape are used (mvoc_b200.synthetic), so the
-script also serves as an offline end-to-end exercise of the config → hooks → loop path.  UNet weights come
-from `--unet_state_dict` (a diffusers I2VGenXLUNet state dict) or are random-initialised.
+image_latents_first / image_latents [n+3,4,T,h,w]); the path may contain `{video_name}` / `{edited_video_name}`
+so that every config entry gets its own file.  Missing inverted latents, masks or conditioning are ERRORS, like
+the reference's asserts (utils.py:34, composite.py:246).  Only with `--synthetic` are seeded synthetic tensors
+of the right shape substituted (mvoc_b200.synthetic) — the offline end-to-end exercise of the config → hooks →
+loop path; the output is then written as `composite_latents.synthetic.pt`.  UNet weights come from
+`--unet_state_dict` (a diffusers I2VGenXLUNet state dict) or, with `--synthetic`, are random-initialised.
 """
 from __future__ import annotations
 
@@ -59,8 +61,15 @@ def latent_geometry(config):
     return int(config.n_frames), int(h_px) // 8, int(w_px) // 8
 
 
-def run_entry(pipe, config, device, conditioning=None):
-    """One config entry -> final composite latents [1,4,T,h,w] (fp32, on `device`)."""
+def conditioning_path(template: str, config) -> str:
+    """`--conditioning` may name one file per entry through {video_name} / {edited_video_name}."""
+    return template.format(video_name=config.video_name,
+                           edited_video_name=config.get("edited_video_name", config.video_name))
+
+
+def run_entry(pipe, config, device, conditioning=None, allow_synthetic: bool = False):
+    """One config entry -> final composite latents [1,4,T,h,w] (fp32, on `device`).  Missing inputs raise
+    FileNotFoundError unless allow_synthetic."""
     from .pipeline import Conditioning, LatentBank, init_pnp
     from .scheduler import DDIMSchedule
     from .utils import mask_preprocess, seed_everything
@@ -77,7 +86,10 @@ def run_entry(pipe, config, device, conditioning=None):
     def bank(path, fallback):
         if path and os.path.isdir(path):
             return LatentBank.from_dir(path, sched.timesteps, device)
-        logger.warning("inverted latents %s not found: using synthetic source latents", path)
+        if not allow_synthetic:
+            raise FileNotFoundError(f"inverted latents directory {path!r} not found (run inverse.py first, or pass "
+                                    "--synthetic for an offline exercise with seeded synthetic latents)")
+        logger.warning("inverted latents %s not found: using synthetic source latents (--synthetic)", path)
         return LatentBank(fallback, device)
 
     bg = bank(config.bg_ddim_latents_path, synth["source_latents"][0])
@@ -89,9 +101,14 @@ def run_entry(pipe, config, device, conditioning=None):
             if tuple(mf.shape[-2:]) != (h, w):
                 raise ValueError(f"mask {p} is {tuple(mf.shape[-2:])} after /8, latents are {(h, w)}")
         else:
-            logger.warning("mask %s not found: using a synthetic mask", p)
+            if not allow_synthetic:
+                raise FileNotFoundError(f"object mask {p!r} not found (pass --synthetic for a synthetic mask)")
+            logger.warning("mask %s not found: using a synthetic mask (--synthetic)", p)
             mf, mb = (t.to(device) for t in synth["masks"][j])
         masks.append((mf, mb))
+    if conditioning is None and not allow_synthetic:
+        raise FileNotFoundError("no --conditioning file for this entry (CLIP / VAE outputs are inputs of this "
+                                "script); pass --synthetic for seeded synthetic conditioning")
     src = conditioning if conditioning is not None else synth
     cond = Conditioning(src["prompt_embeds"].to(device, dt), src["image_embeddings"].to(device, dt),
                         src["image_latents_first"].to(device, dt), src["image_latents"].to(device, dt),
@@ -106,26 +123,36 @@ def run_entry(pipe, config, device, conditioning=None):
 
 
 def main(template_config: str, configs_json: str, unet_state_dict: str = None, conditioning: str = None,
-         device: str = None, max_entries: int = None):
+         device: str = None, max_entries: int = None, synthetic_inputs: bool = False):
     from .pipeline import I2VGenXLPipeline
     from .unet3d import I2VGenXLUNet, UNetConfig, prepare
 
     template = cfgmod.load_template(template_config)
     device = torch.device(device or template.get("device", "cuda:0"))
+    if device.type == "cuda":
+        torch.cuda.set_device(device)      # the C-ABI launches on the current device (mvoc_b200.ops._need_cuda)
     torch.set_grad_enabled(False)                                               # composite.py:253
     unet = I2VGenXLUNet(UNetConfig.full()).eval().requires_grad_(False)
     if unet_state_dict:
         unet.load_state_dict(torch.load(unet_state_dict, map_location="cpu"), strict=True)
+    elif not synthetic_inputs:
+        raise FileNotFoundError("--unet_state_dict is required (pass --synthetic to run on random-init weights)")
     unet = prepare(unet.to(device=device, dtype=torch.bfloat16))
     pipe = I2VGenXLPipeline(unet, device, use_cuda_graphs=True)
-    cond = torch.load(conditioning, map_location="cpu") if conditioning else None
     done = 0
     for config in cfgmod.iter_configs(template_config, configs_json):
         config = resolve_paths(config)
         logger.info("Processing %s / %s", config.video_name, config.edited_video_name)
-        latents = run_entry(pipe, config, device, cond)
+        cond = None
+        if conditioning:
+            cpath = conditioning_path(conditioning, config)
+            if not os.path.exists(cpath):
+                raise FileNotFoundError(f"conditioning file {cpath!r} not found")
+            cond = torch.load(cpath, map_location="cpu")
+        latents = run_entry(pipe, config, device, cond, allow_synthetic=synthetic_inputs)
         os.makedirs(config.output_dir, exist_ok=True)
-        out = os.path.join(config.output_dir, "composite_latents.pt")
+        out = os.path.join(config.output_dir,
+                           "composite_latents.synthetic.pt" if synthetic_inputs else "composite_latents.pt")
         torch.save(latents.detach().cpu(), out)
         logger.info("saved %s", out)
         done += 1
@@ -142,6 +169,8 @@ def build_parser() -> argparse.ArgumentParser:
     ap.add_argument("--conditioning", type=str, default=None)
     ap.add_argument("--device", type=str, default=None)
     ap.add_argument("--max_entries", type=int, default=None)
+    ap.add_argument("--synthetic", action="store_true",
+                    help="substitute seeded synthetic tensors for missing latents / masks / conditioning / weights")
     return ap
 
 
@@ -150,4 +179,4 @@ if __name__ == "__main__":
     logging.basicConfig(level=logging.INFO)
     assert os.path.exists(args.template_config) and os.path.exists(args.configs_json)   # composite.py:246
     main(args.template_config, args.configs_json, args.unet_state_dict, args.conditioning, args.device,
-         args.max_entries)
+         args.max_entries, args.synthetic)

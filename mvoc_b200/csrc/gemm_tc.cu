@@ -1,0 +1,768 @@
+// Dense work of the UNet on tcgen05 tensor cores: 3x3 convolutions, temporal (3,1,1) convolutions
+// and every Linear / 1x1 conv as ONE persistent, warp-specialised implicit-GEMM kernel on channels-last bf16 / fp16
+// activations.  Replaces what the reference leaves to cuDNN / cuBLAS:
+//   resnet conv1 / conv2 (+ 1x1 shortcut, + residual)      i2vgen-xl/pnp_utils.py:939, :968, :1011-1018
+//   TemporalConvLayer conv1..4 (+ identity)                 i2vgen-xl/pnp_utils.py:1048-1053
+//   to_q / to_k / to_v / to_out, proj_in / proj_out         i2vgen-xl/pnp_utils.py:604-612, :692, :191, :206, :432, :503
+//   GEGLU feed-forward                                      i2vgen-xl/pnp_utils.py:335
+//
+// Formulation.  out[row, n] = sum_{src, tap, k} A_src[row + shift(tap), k] * W_src[tap, n, k]  (+ bias[n]) (+ residual)
+// where the rows of A are the pixels of a channels-last activation viewed as a 4-D tensor [K, d1, d2, d3]:
+//   conv3x3     : [Cin, W, H, N], 9 taps shifting (d1, d2) by (-1..1, -1..1)
+//   temporal    : [Cin, S, T, B], 3 taps shifting d2 (the frame) by -1..1
+//   linear      : [K, M, 1, 1],   1 tap
+// A tile of 128 rows is a TMA box {64 channels, b1, b2, b3} whose start coordinate is moved by the tap shift;
+// rows that fall outside the tensor are ZERO-FILLED by TMA, which IS the convolution's padding — no im2col
+// buffer, no halo copy.  A second (A, W) source appended to the K loop fuses the resnet's 1x1 shortcut conv
+// into conv2's accumulator.
+//
+// CTA (192 threads, one per SM, persistent over tiles, static round-robin schedule):
+//   warp 0     TMA producer: ring of kStages {A 128x64, W BNx64} 128-byte-swizzled stages
+//   warp 1     MMA issuer (one lane): tcgen05.mma 128 x BN x 16 into one of TWO accumulator buffers in TMEM,
+//              so the epilogue of tile i overlaps the main loop of tile i+1; owns the TMEM allocation
+//   warps 2-5  epilogue: thread = TMEM lane = output row; 32-column slabs: tcgen05.ld -> + bias -> (+ residual,
+//              TMA-loaded into the staging buffer one slab ahead) -> (GEGLU) -> bf16 -> swizzled smem -> TMA store
+// kTwoCta: the same kernel as a CTA PAIR (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, each
+// CTA stages its own 128 rows of A and HALF of the weight tile, the leader issues M = 256 MMAs that read both
+// halves — weight traffic from L2 per CTA halves.
+#include <cuda.h>
+#include <type_traits>
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mvoc {
+namespace gemm {
+
+constexpr int BM = 128;                    // rows (pixels) per CTA tile
+constexpr int KC = 64;                     // K elements per stage = one 128-byte swizzled row
+constexpr int A_BYTES = BM * KC * 2;       // 16 KB
+constexpr int SLAB = 32;                   // output columns per epilogue slab (64-byte rows, 64B swizzle)
+constexpr int SLAB_BYTES = BM * SLAB * 2;  // 8 KB
+constexpr int N_OUT = 4;                   // staging buffers of the epilogue
+constexpr int THREADS = 192;
+constexpr int SMEM_LIMIT = 232448;         // 227 KB per CTA
+constexpr uint32_t TMEM_COLS = 512;
+constexpr int MAX_TAPS = 9;
+
+enum Epilogue { EPI_LINEAR = 0, EPI_GEGLU = 1 };
+
+template <int BN_, bool kTwoCta_, int kEpi_>
+struct Cfg {
+    static constexpr int BN = BN_;
+    static constexpr bool kTwoCta = kTwoCta_;
+    static constexpr int kEpi = kEpi_;
+    static constexpr int B_ROWS = kTwoCta ? BN / 2 : BN;     // weight rows THIS CTA stages
+    static constexpr int B_BYTES = B_ROWS * KC * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int OUT_COLS = kEpi == EPI_GEGLU ? BN / 2 : BN;   // output columns of a tile
+    static constexpr int SLABS = OUT_COLS / SLAB;
+    static constexpr int out_off = 0;                        // staging first: 1024-byte aligned like the stages
+    static constexpr int stage_off = N_OUT * SLAB_BYTES;
+    static constexpr int kStagesFit = (SMEM_LIMIT - stage_off - 512) / STAGE_BYTES;
+    static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+    static constexpr int bar_off = stage_off + kStages * STAGE_BYTES;
+    // barriers: full[kStages], empty[kStages], acc_full[2], acc_empty[2], res_full[N_OUT]
+    static constexpr int n_bars = 2 * kStages + 4 + N_OUT;
+    static constexpr int tmem_ptr_off = bar_off + n_bars * 8;
+    static constexpr int alloc = tmem_ptr_off + 16;
+    static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "BN: multiple of 32 in [64, 256]");
+    static_assert(OUT_COLS % SLAB == 0, "tile columns must be whole slabs");
+    static_assert(B_BYTES % 1024 == 0, "weight stage must keep the 1024-byte swizzle-atom alignment");
+    static_assert(kStages >= 3, "too few pipeline stages");
+    static_assert(alloc <= SMEM_LIMIT, "shared memory budget exceeded");
+    static_assert(2 * BN <= (int)TMEM_COLS, "two accumulator buffers must fit in TMEM");
+};
+
+struct Params {
+    int total_tiles;           // tiles (1-CTA) or tile PAIRS (2-CTA) of the whole problem
+    int n_tiles;               // column tiles
+    int t1, t2;                // row tiles along d1 and d2 (d3 follows)
+    int b1, b2, b3;            // row box, b1 * b2 * b3 == 128
+    int n_src;                 // 1 or 2 (A, W) sources in the K loop
+    int k_chunks[2];           // K / 64 per source
+    int taps[2];
+    int8_t off[2][MAX_TAPS][3];   // coordinate shift of (d1, d2, d3) per tap
+    int gate_off;              // GEGLU: row of W where the gate half starts (F)
+    int has_res;
+    const void* bias;          // [N] (GEGLU: [2F]) in the activation dtype, or nullptr
+};
+
+// ---- PTX pieces this kernel adds to ptx.cuh --------------------------------------------------------------------
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared::cluster address in a CTA pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+template <bool kTwoCta>
+__device__ __forceinline__ void tma_load_tile(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2,
+                                              int c3) {
+    if (kTwoCta) {
+        // executed by both CTAs of the pair; the transaction bytes land on the LEADER's barrier
+        asm volatile(
+            "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+            "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+            "l"(tmap), "r"(bar & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+            : "memory");
+    } else {
+        ptx::tma_load_4d(dst, tmap, bar, c0, c1, c2, c3);
+    }
+}
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap),
+                 "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+template <int N> __device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // arrive on the pair leader's barrier
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_MASK) : "memory");
+}
+template <bool kTwoCta> __device__ __forceinline__ void tmem_alloc_t(uint32_t smem_dst, uint32_t ncols) {
+    if (kTwoCta) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+        ptx::tmem_alloc(smem_dst, ncols);
+        ptx::tmem_relinquish();
+    }
+}
+template <bool kTwoCta> __device__ __forceinline__ void tmem_dealloc_t(uint32_t taddr, uint32_t ncols) {
+    if (kTwoCta)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+    else
+        ptx::tmem_dealloc(taddr, ncols);
+}
+template <bool kTwoCta>
+__device__ __forceinline__ void mma_t(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                      uint32_t accumulate) {
+    if (kTwoCta) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        ptx::mma_ss(d_tmem, a_desc, b_desc, idesc, accumulate);
+    }
+}
+// mbarrier arrive once the MMAs issued so far have completed; pair mode: on this barrier in BOTH CTAs
+template <bool kTwoCta> __device__ __forceinline__ void commit_t(uint32_t bar) {
+    if (kTwoCta) {
+        asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                bar),
+            "h"((uint16_t)0x3)
+            : "memory");
+    } else {
+        ptx::tc_commit(bar);
+    }
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ Vec16 lds16(uint32_t addr) {
+    Vec16 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, const Vec16& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3])
+                 : "memory");
+}
+__device__ __forceinline__ Vec16 ldg16_nc(const void* p) {
+    Vec16 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p));
+    return v;
+}
+
+// Instruction descriptor kind::f16: 16-bit inputs (kF16 ? fp16 : bf16), fp32 accumulation, A and B K-major.
+__host__ __device__ constexpr uint32_t idesc_16(int M, int N, bool f16) {
+    return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+struct TileCoord {
+    int n_tile, c1, c2, c3;
+};
+
+template <typename C>
+__device__ __forceinline__ TileCoord decode_tile(const Params& p, int t, uint32_t crank) {
+    TileCoord tc;
+    tc.n_tile = t % p.n_tiles;
+    int m = t / p.n_tiles;
+    if (C::kTwoCta) m = 2 * m + (int)crank;
+    const int i1 = m % p.t1;
+    m /= p.t1;
+    const int i2 = m % p.t2;
+    const int i3 = m / p.t2;            // may run past the tensor for the padding tile of an odd pair: all OOB
+    tc.c1 = i1 * p.b1;
+    tc.c2 = i2 * p.b2;
+    tc.c3 = i3 * p.b3;
+    return tc;
+}
+
+template <typename C, typename T>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_w0,
+               const __grid_constant__ CUtensorMap tm_a1, const __grid_constant__ CUtensorMap tm_w1,
+               const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
+               const Params prm) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t sbase = smem_u32(smem_raw);
+    if ((sbase & 1023u) != 0u) {
+        if (threadIdx.x == 0) printf("mvoc gemm_tc_kernel: dynamic smem base 0x%x is not 1024-byte aligned\n", sbase);
+        __trap();
+    }
+    constexpr int kStages = C::kStages;
+    const uint32_t sOut = sbase + C::out_off;
+    const uint32_t sStage = sbase + C::stage_off;
+    const uint32_t bars = sbase + C::bar_off;
+    const uint32_t b_full = bars, b_empty = bars + 8 * kStages, b_acc_full = bars + 16 * kStages,
+                   b_acc_empty = b_acc_full + 16, b_res = b_acc_empty + 16;
+    const uint32_t s_tmem_ptr = sbase + C::tmem_ptr_off;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = C::kTwoCta ? cluster_ctarank() : 0u;
+    const bool leader = crank == 0;
+    const int first_tile = C::kTwoCta ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_stride = C::kTwoCta ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tm_a0);
+        ptx::prefetch_tensormap(&tm_w0);
+        ptx::prefetch_tensormap(&tm_out);
+        if (prm.n_src > 1) {
+            ptx::prefetch_tensormap(&tm_a1);
+            ptx::prefetch_tensormap(&tm_w1);
+        }
+        if (prm.has_res) ptx::prefetch_tensormap(&tm_res);
+        for (int s = 0; s < kStages; ++s) {
+            ptx::mbar_init(b_full + 8 * s, 1);
+            ptx::mbar_init(b_empty + 8 * s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            ptx::mbar_init(b_acc_full + 8 * b, 1);
+            ptx::mbar_init(b_acc_empty + 8 * b, C::kTwoCta ? 8 : 4);   // one arrive per epilogue warp (of both CTAs)
+        }
+        for (int b = 0; b < N_OUT; ++b) ptx::mbar_init(b_res + 8 * b, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_t<C::kTwoCta>(s_tmem_ptr, TMEM_COLS);
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (C::kTwoCta) cluster_sync_all();   // the peer's barriers exist before anything is signalled on them
+    ptx::tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem_raw + C::tmem_ptr_off);
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = first_tile; t < prm.total_tiles; t += tile_stride) {
+                const TileCoord tc = decode_tile<C>(prm, t, crank);
+                for (int src = 0; src < prm.n_src; ++src) {
+                    const CUtensorMap* ma = src ? &tm_a1 : &tm_a0;
+                    const CUtensorMap* mw = src ? &tm_w1 : &tm_w0;
+                    const int taps = prm.taps[src];
+                    for (int kc = 0; kc < prm.k_chunks[src]; ++kc)
+                        for (int tap = 0; tap < taps; ++tap, ++it) {   // taps innermost: shifted boxes share L2 lines
+                            const uint32_t s = it % kStages;
+                            const uint32_t ph = (it / kStages) & 1u;
+                            ptx::mbar_wait(b_empty + 8 * s, ph ^ 1u, 1);
+                            const uint32_t sA = sStage + s * C::STAGE_BYTES, sB = sA + A_BYTES;
+                            const uint32_t full = b_full + 8 * s;
+                            if (!C::kTwoCta) ptx::mbar_expect_tx(full, C::STAGE_BYTES);
+                            else if (leader) ptx::mbar_expect_tx(full, 2 * C::STAGE_BYTES);
+                            tma_load_tile<C::kTwoCta>(sA, ma, full, kc * KC, tc.c1 + prm.off[src][tap][0],
+                                                      tc.c2 + prm.off[src][tap][1], tc.c3 + prm.off[src][tap][2]);
+                            if (C::kEpi == EPI_GEGLU) {
+                                // accumulator columns = NP value columns then NP gate columns of the same Linear
+                                constexpr int NP = C::BN / 2;
+                                if (C::kTwoCta) {   // leader stages the value rows, the peer the gate rows
+                                    const int wrow = tc.n_tile * NP + (leader ? 0 : prm.gate_off);
+                                    tma_load_tile<true>(sB, mw, full, kc * KC, wrow, tap, 0);
+                                } else {
+                                    tma_load_tile<false>(sB, mw, full, kc * KC, tc.n_tile * NP, tap, 0);
+                                    tma_load_tile<false>(sB + NP * KC * 2, mw, full, kc * KC,
+                                                         tc.n_tile * NP + prm.gate_off, tap, 0);
+                                }
+                            } else {
+                                const int wrow = tc.n_tile * C::BN + (C::kTwoCta ? (int)crank * C::B_ROWS : 0);
+                                tma_load_tile<C::kTwoCta>(sB, mw, full, kc * KC, wrow, tap, 0);
+                            }
+                        }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (pair mode: the leader CTA only) =====================
+        if (lane == 0 && leader) {
+            constexpr bool kF16 = sizeof(T) == 2 && !std::is_same<T, __nv_bfloat16>::value;
+            constexpr uint32_t IDESC = idesc_16(C::kTwoCta ? 256 : 128, C::BN, kF16);
+            uint32_t it = 0, lt = 0;
+            for (int t = first_tile; t < prm.total_tiles; t += tile_stride, ++lt) {
+                const uint32_t buf = lt & 1u;
+                ptx::mbar_wait(b_acc_empty + 8 * buf, ((lt >> 1) & 1u) ^ 1u, 2);
+                ptx::tc_fence_after();
+                const uint32_t tacc = tmem + buf * C::BN;
+                int n_chunks = 0;
+                for (int src = 0; src < prm.n_src; ++src) n_chunks += prm.k_chunks[src] * prm.taps[src];
+                for (int c = 0; c < n_chunks; ++c, ++it) {
+                    const uint32_t s = it % kStages;
+                    const uint32_t ph = (it / kStages) & 1u;
+                    ptx::mbar_wait(b_full + 8 * s, ph, 3);
+                    ptx::tc_fence_after();
+                    const uint32_t sA = sStage + s * C::STAGE_BYTES, sB = sA + A_BYTES;
+                    const uint64_t a0 = ptx::smem_desc_sw128(sA, 16, 1024);
+                    const uint64_t b0 = ptx::smem_desc_sw128(sB, 16, 1024);
+#pragma unroll
+                    for (int ks = 0; ks < KC / 16; ++ks)   // +32 B per 16-element K step (encoded >> 4)
+                        mma_t<C::kTwoCta>(tacc, a0 + (uint64_t)(ks * 2), b0 + (uint64_t)(ks * 2), IDESC,
+                                          (c > 0 || ks > 0) ? 1u : 0u);
+                    commit_t<C::kTwoCta>(b_empty + 8 * s);   // stage reusable once these MMAs have read it
+                }
+                commit_t<C::kTwoCta>(b_acc_full + 8 * buf);   // accumulator complete (both CTAs in pair mode)
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2-5) =====================
+        const int q = warp & 3;                        // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;                 // row of the tile == TMEM lane
+        const bool issuer = threadIdx.x == 64;         // warp 2, lane 0: owns the bulk-async groups
+        const uint32_t row_off = (uint32_t)row * 64u;
+        const uint32_t sw = (uint32_t)((row >> 1) & 3);   // 64-byte swizzle: 16-byte chunk c lives at c ^ sw
+        const T* bias = reinterpret_cast<const T*>(prm.bias);
+
+        // slab g of this CTA -> (valid, output column, row coordinates)
+        auto slab_at = [&](uint32_t g, int& col, TileCoord& tc) -> bool {
+            const int t = first_tile + (int)(g / C::SLABS) * tile_stride;
+            if (t >= prm.total_tiles) return false;
+            tc = decode_tile<C>(prm, t, crank);
+            col = tc.n_tile * C::OUT_COLS + (int)(g % C::SLABS) * SLAB;
+            return true;
+        };
+        auto prefetch_res = [&](uint32_t g) {
+            int col;
+            TileCoord tc;
+            if (!slab_at(g, col, tc)) return;
+            const uint32_t ob = g % N_OUT;
+            ptx::mbar_expect_tx(b_res + 8 * ob, SLAB_BYTES);
+            ptx::tma_load_4d(sOut + ob * SLAB_BYTES, &tm_res, b_res + 8 * ob, col, tc.c1, tc.c2, tc.c3);
+        };
+        if (issuer && prm.has_res) {
+            prefetch_res(0);
+            prefetch_res(1);
+        }
+        uint32_t g = 0, lt = 0;
+        for (int t = first_tile; t < prm.total_tiles; t += tile_stride, ++lt) {
+            const TileCoord tc = decode_tile<C>(prm, t, crank);
+            const uint32_t buf = lt & 1u;
+            ptx::mbar_wait(b_acc_full + 8 * buf, (lt >> 1) & 1u, 4);
+            ptx::tc_fence_after();
+            const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + buf * C::BN;
+            const int col0 = tc.n_tile * C::OUT_COLS;
+#pragma unroll 1
+            for (int sl = 0; sl < C::SLABS; ++sl, ++g) {
+                const uint32_t ob = g % N_OUT;
+                const uint32_t sbuf = sOut + ob * SLAB_BYTES + row_off;
+                uint32_t r[32];
+                ptx::tmem_ld32(tacc + sl * SLAB, r);
+                uint32_t gt[32];
+                if (C::kEpi == EPI_GEGLU) ptx::tmem_ld32(tacc + C::BN / 2 + sl * SLAB, gt);
+                ptx::tmem_wait_ld();
+                if (sl == C::SLABS - 1) {   // accumulator buffer drained: hand it back to the MMA warp
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (C::kTwoCta) mbar_arrive_leader(b_acc_empty + 8 * buf);
+                        else ptx::mbar_arrive(b_acc_empty + 8 * buf);
+                    }
+                }
+                if (prm.has_res) ptx::mbar_wait(b_res + 8 * ob, (g / N_OUT) & 1u, 5);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[c * 8 + e]);
+                    if (bias) {
+                        float bv[8];
+                        unpack8<T>(ldg16_nc(bias + col0 + sl * SLAB + c * 8), bv);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] += bv[e];
+                    }
+                    if (C::kEpi == EPI_GEGLU) {
+                        float gv[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) gv[e] = __uint_as_float(gt[c * 8 + e]);
+                        if (bias) {
+                            float bg[8];
+                            unpack8<T>(ldg16_nc(bias + prm.gate_off + col0 + sl * SLAB + c * 8), bg);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) gv[e] += bg[e];
+                        }
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)   // exact (erf) GELU, as torch.nn.functional.gelu
+                            f[e] *= 0.5f * gv[e] * (1.0f + erff(gv[e] * 0.70710678118654752f));
+                    }
+                    const uint32_t addr = sbuf + (((uint32_t)c ^ sw) << 4);
+                    if (prm.has_res) {
+                        float rv[8];
+                        unpack8<T>(lds16(addr), rv);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] += rv[e];
+                    }
+                    sts16(addr, pack8<T>(f));
+                }
+                ptx::fence_proxy_async_smem();          // generic-proxy writes -> visible to the TMA store
+                if (issuer) bulk_wait_read<1>();        // the store of slab g-2 has released its buffer
+                named_bar_sync(1, 128);
+                if (issuer) {
+                    tma_store_4d(&tm_out, sOut + ob * SLAB_BYTES, col0 + sl * SLAB, tc.c1, tc.c2, tc.c3);
+                    ptx::bulk_commit();
+                    if (prm.has_res) prefetch_res(g + 2);   // into the buffer slab g-2 used
+                }
+            }
+        }
+        if (issuer) bulk_wait_all();
+        ptx::tc_fence_before();
+    }
+
+    __syncthreads();
+    if (C::kTwoCta) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while its peer may still use it
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        tmem_dealloc_t<C::kTwoCta>(tmem, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------ host ---
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 4-D 16-bit tensor map: dims / box innermost first, strides (elements) of dims 1..3; zero OOB fill.
+static int make_map4(CUtensorMap* m, const void* base, int dtype, const int64_t (&dims)[4], const int64_t (&str)[3],
+                     const int (&box)[4], CUtensorMapSwizzle swz, const char* what) {
+    EncodeTiledFn fn = get_encode_fn();
+    MVOC_REQUIRE(fn != nullptr, MVOC_ERR_DRIVER, "%s: cuTensorMapEncodeTiled unavailable", what);
+    cuuint64_t d[4], s[3];
+    cuuint32_t b[4], estr[4] = {1, 1, 1, 1};
+    for (int i = 0; i < 4; ++i) d[i] = (cuuint64_t)dims[i], b[i] = (cuuint32_t)box[i];
+    for (int i = 0; i < 3; ++i) {
+        s[i] = (cuuint64_t)str[i] * 2;
+        if (dims[i + 1] == 1 && (s[i] == 0 || s[i] % 16 != 0)) s[i] = (i == 0 ? d[0] * 2 : s[i - 1] * d[i]);
+        MVOC_REQUIRE(s[i] % 16 == 0, MVOC_ERR_UNSUPPORTED, "%s: stride %lld elements is not a multiple of 8", what,
+                     (long long)str[i]);
+    }
+    CUresult r = fn(m, dtype == MVOC_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                    const_cast<void*>(base), d, s, b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MVOC_REQUIRE(r == CUDA_SUCCESS, MVOC_ERR_DRIVER,
+                 "%s: cuTensorMapEncodeTiled failed with CUresult %d (dims %lld,%lld,%lld,%lld strides %lld,%lld,%lld "
+                 "box %d,%d,%d,%d)",
+                 what, (int)r, (long long)dims[0], (long long)dims[1], (long long)dims[2], (long long)dims[3],
+                 (long long)str[0], (long long)str[1], (long long)str[2], box[0], box[1], box[2], box[3]);
+    return MVOC_OK;
+}
+
+static int pow2_floor(int64_t v) {
+    int p = 1;
+    while ((int64_t)p * 2 <= v) p *= 2;
+    return p;
+}
+
+// Row box (b1, b2, b3), powers of two with product 128, that wastes the fewest zero-filled rows on the
+// (d1, d2, d3) grid; ties go to the widest box along d1 (longest contiguous runs).
+static void choose_box(int64_t d1, int64_t d2, int64_t d3, int* b1, int* b2, int* b3) {
+    int64_t best = -1;
+    for (int w = 128; w >= 1; w >>= 1)
+        for (int h = 128 / w; h >= 1; h >>= 1) {
+            const int n = 128 / (w * h);
+            const int64_t padded = ((d1 + w - 1) / w) * w * ((d2 + h - 1) / h) * h * ((d3 + n - 1) / n) * n;
+            if (best < 0 || padded < best) {
+                best = padded;
+                *b1 = w, *b2 = h, *b3 = n;
+            }
+        }
+}
+
+// One (activation, weight) source of the K loop.
+struct Source {
+    const void* a;
+    int64_t K;                 // channels (multiple of 64)
+    int64_t a_str[3];          // element strides of d1, d2, d3
+    const void* w;             // [taps, n_rows, K] contiguous
+    int taps;
+    int8_t off[MAX_TAPS][3];
+};
+
+struct Problem {
+    int dtype;
+    int64_t d1, d2, d3;        // row grid
+    int n_src;
+    Source src[2];
+    int64_t N;                 // output columns (GEGLU: F)
+    int64_t w_rows;            // rows of each weight tap (N, GEGLU: 2F)
+    const void* bias;
+    const void* residual;
+    int64_t res_str[3];
+    void* out;
+    int64_t out_str[3];
+    int geglu;
+    int variant;               // bit 0: CTA pairs; bits 8..15: BN override (0 = auto)
+    const char* what;
+};
+
+template <typename C, typename T>
+static int launch_cfg(const Problem& pb, Params prm, int b1, int b2, int b3, cudaStream_t stream) {
+    const char* what = pb.what;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<C, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::alloc);
+        MVOC_REQUIRE(e == cudaSuccess, MVOC_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+        attr_set[dev] = true;
+    }
+    CUtensorMap ma[2], mw[2], mo, mr;
+    int rc;
+    for (int s = 0; s < pb.n_src; ++s) {
+        const Source& sc = pb.src[s];
+        const int64_t dims[4] = {sc.K, pb.d1, pb.d2, pb.d3};
+        const int box[4] = {KC, b1, b2, b3};
+        if ((rc = make_map4(&ma[s], sc.a, pb.dtype, dims, sc.a_str, box, CU_TENSOR_MAP_SWIZZLE_128B, what)) != MVOC_OK)
+            return rc;
+        const int64_t wd[4] = {sc.K, pb.w_rows, sc.taps, 1};
+        const int64_t ws[3] = {sc.K, sc.K * pb.w_rows, sc.K * pb.w_rows * sc.taps};
+        const int wb[4] = {KC, C::kEpi == EPI_GEGLU ? C::BN / 2 : C::B_ROWS, 1, 1};
+        if ((rc = make_map4(&mw[s], sc.w, pb.dtype, wd, ws, wb, CU_TENSOR_MAP_SWIZZLE_128B, what)) != MVOC_OK) return rc;
+    }
+    if (pb.n_src == 1) ma[1] = ma[0], mw[1] = mw[0];
+    {
+        const int64_t dims[4] = {pb.N, pb.d1, pb.d2, pb.d3};
+        const int box[4] = {SLAB, b1, b2, b3};
+        if ((rc = make_map4(&mo, pb.out, pb.dtype, dims, pb.out_str, box, CU_TENSOR_MAP_SWIZZLE_64B, what)) != MVOC_OK)
+            return rc;
+        if (pb.residual) {
+            if ((rc = make_map4(&mr, pb.residual, pb.dtype, dims, pb.res_str, box, CU_TENSOR_MAP_SWIZZLE_64B, what)) !=
+                MVOC_OK)
+                return rc;
+        } else {
+            mr = mo;
+        }
+    }
+    prm.n_tiles = (int)(pb.N / C::OUT_COLS);
+    const int64_t m_tiles = (int64_t)prm.t1 * prm.t2 * ((pb.d3 + b3 - 1) / b3);
+    const int64_t units = C::kTwoCta ? (m_tiles + 1) / 2 : m_tiles;
+    const int64_t total = units * prm.n_tiles;
+    MVOC_REQUIRE(total > 0 && total <= 0x7fffffffLL, MVOC_ERR_UNSUPPORTED, "%s: %lld tiles", what, (long long)total);
+    prm.total_tiles = (int)total;
+    const int sms = num_sms();
+    int64_t ctas = C::kTwoCta ? 2 * (total < sms / 2 ? total : sms / 2) : (total < sms ? total : sms);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = C::alloc;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C::kTwoCta ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<C, T>, ma[0], mw[0], ma[1], mw[1], mo, mr, prm);
+    MVOC_REQUIRE(e == cudaSuccess, MVOC_ERR_CUDA, "%s: launch failed: %s", what, cudaGetErrorString(e));
+    return MVOC_OK;
+}
+
+template <int BN, int kEpi>
+static int launch_bn(const Problem& pb, const Params& prm, int b1, int b2, int b3, cudaStream_t s) {
+    const bool two = (pb.variant & 1) != 0;
+    if (pb.dtype == MVOC_F16) {
+        if (two) return launch_cfg<Cfg<BN, true, kEpi>, __half>(pb, prm, b1, b2, b3, s);
+        return launch_cfg<Cfg<BN, false, kEpi>, __half>(pb, prm, b1, b2, b3, s);
+    }
+    if (two) return launch_cfg<Cfg<BN, true, kEpi>, __nv_bfloat16>(pb, prm, b1, b2, b3, s);
+    return launch_cfg<Cfg<BN, false, kEpi>, __nv_bfloat16>(pb, prm, b1, b2, b3, s);
+}
+
+static int run(const Problem& pb, cudaStream_t stream) {
+    const char* what = pb.what;
+    MVOC_REQUIRE(pb.dtype == MVOC_BF16 || pb.dtype == MVOC_F16, MVOC_ERR_UNSUPPORTED,
+                 "%s: dtype %d unsupported (bf16 / fp16)", what, pb.dtype);
+    MVOC_REQUIRE(pb.d1 > 0 && pb.d2 > 0 && pb.d3 > 0, MVOC_ERR_INVALID_ARG, "%s: empty row grid %lld x %lld x %lld", what,
+                 (long long)pb.d1, (long long)pb.d2, (long long)pb.d3);
+    MVOC_REQUIRE(pb.d1 <= 0x7fffffffLL && pb.d2 <= 0x7fffffffLL && pb.d3 <= 0x7fffffffLL, MVOC_ERR_UNSUPPORTED,
+                 "%s: row grid too large", what);
+    MVOC_REQUIRE(pb.N > 0 && pb.N % 64 == 0, MVOC_ERR_UNSUPPORTED, "%s: N=%lld must be a multiple of 64", what,
+                 (long long)pb.N);
+    MVOC_REQUIRE(pb.out != nullptr && (uintptr_t)pb.out % 16 == 0 && (uintptr_t)pb.bias % 16 == 0 &&
+                     (uintptr_t)pb.residual % 16 == 0,
+                 MVOC_ERR_INVALID_ARG, "%s: out / bias / residual must be non-null (out) and 16-byte aligned", what);
+    Params prm{};
+    prm.n_src = pb.n_src;
+    for (int s = 0; s < pb.n_src; ++s) {
+        const Source& sc = pb.src[s];
+        MVOC_REQUIRE(sc.a && sc.w && (uintptr_t)sc.a % 16 == 0 && (uintptr_t)sc.w % 16 == 0, MVOC_ERR_INVALID_ARG,
+                     "%s: activation / weight pointers must be non-null and 16-byte aligned", what);
+        MVOC_REQUIRE(sc.K > 0 && sc.K % 64 == 0, MVOC_ERR_UNSUPPORTED, "%s: K=%lld must be a multiple of 64", what,
+                     (long long)sc.K);
+        MVOC_REQUIRE(sc.taps >= 1 && sc.taps <= MAX_TAPS, MVOC_ERR_INVALID_ARG, "%s: %d taps", what, sc.taps);
+        prm.k_chunks[s] = (int)(sc.K / 64);
+        prm.taps[s] = sc.taps;
+        for (int t = 0; t < sc.taps; ++t)
+            for (int d = 0; d < 3; ++d) prm.off[s][t][d] = sc.off[t][d];
+    }
+    int b1, b2, b3;
+    choose_box(pb.d1, pb.d2, pb.d3, &b1, &b2, &b3);
+    prm.b1 = b1, prm.b2 = b2, prm.b3 = b3;
+    prm.t1 = (int)((pb.d1 + b1 - 1) / b1);
+    prm.t2 = (int)((pb.d2 + b2 - 1) / b2);
+    prm.bias = pb.bias;
+    prm.has_res = pb.residual != nullptr;
+    prm.gate_off = (int)pb.N;
+    int BN = (pb.variant >> 8) & 0x1ff;
+    if (pb.geglu) {
+        if (BN == 0) BN = pb.N % 128 == 0 ? 256 : 128;
+        MVOC_REQUIRE((BN == 256 || BN == 128) && pb.N % (BN / 2) == 0, MVOC_ERR_UNSUPPORTED,
+                     "%s: GEGLU tile %d does not divide F=%lld", what, BN, (long long)pb.N);
+        if (BN == 256) return launch_bn<256, EPI_GEGLU>(pb, prm, b1, b2, b3, stream);
+        return launch_bn<128, EPI_GEGLU>(pb, prm, b1, b2, b3, stream);
+    }
+    if (BN == 0) BN = pb.N % 256 == 0 ? 256 : pb.N % 192 == 0 ? 192 : pb.N % 160 == 0 ? 160 : pb.N % 128 == 0 ? 128 : 64;
+    MVOC_REQUIRE(pb.N % BN == 0, MVOC_ERR_UNSUPPORTED, "%s: tile width %d does not divide N=%lld", what, BN,
+                 (long long)pb.N);
+    switch (BN) {
+        case 256: return launch_bn<256, EPI_LINEAR>(pb, prm, b1, b2, b3, stream);
+        case 192: return launch_bn<192, EPI_LINEAR>(pb, prm, b1, b2, b3, stream);
+        case 160: return launch_bn<160, EPI_LINEAR>(pb, prm, b1, b2, b3, stream);
+        case 128: return launch_bn<128, EPI_LINEAR>(pb, prm, b1, b2, b3, stream);
+        case 64: return launch_bn<64, EPI_LINEAR>(pb, prm, b1, b2, b3, stream);
+        default: break;
+    }
+    set_error("%s: unsupported tile width %d (256, 192, 160, 128, 64)", what, BN);
+    return MVOC_ERR_UNSUPPORTED;
+}
+
+}  // namespace gemm
+}  // namespace mvoc
+
+using namespace mvoc;
+
+extern "C" int mvoc_conv3x3_nhwc(const void* x, const void* w_taps, const void* bias, const void* residual,
+                                 const void* x2, const void* w2, int Cin2, void* out, int N, int H, int W, int Cin,
+                                 int Cout, int dtype, int variant, void* stream) {
+    gemm::Problem pb{};
+    pb.what = "mvoc_conv3x3_nhwc";
+    MVOC_REQUIRE(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, MVOC_ERR_INVALID_ARG,
+                 "%s: empty problem N=%d H=%d W=%d Cin=%d Cout=%d", pb.what, N, H, W, Cin, Cout);
+    MVOC_REQUIRE((x2 == nullptr) == (w2 == nullptr), MVOC_ERR_INVALID_ARG, "%s: x2 and w2 go together", pb.what);
+    pb.dtype = dtype;
+    pb.d1 = W, pb.d2 = H, pb.d3 = N;
+    pb.n_src = x2 ? 2 : 1;
+    gemm::Source& s0 = pb.src[0];
+    s0.a = x, s0.K = Cin, s0.w = w_taps, s0.taps = 9;
+    s0.a_str[0] = Cin, s0.a_str[1] = (int64_t)W * Cin, s0.a_str[2] = (int64_t)H * W * Cin;
+    for (int t = 0; t < 9; ++t) s0.off[t][0] = (int8_t)(t % 3 - 1), s0.off[t][1] = (int8_t)(t / 3 - 1), s0.off[t][2] = 0;
+    if (x2) {
+        gemm::Source& s1 = pb.src[1];
+        s1.a = x2, s1.K = Cin2, s1.w = w2, s1.taps = 1;
+        s1.a_str[0] = Cin2, s1.a_str[1] = (int64_t)W * Cin2, s1.a_str[2] = (int64_t)H * W * Cin2;
+        s1.off[0][0] = s1.off[0][1] = s1.off[0][2] = 0;
+    }
+    pb.N = Cout, pb.w_rows = Cout;
+    pb.bias = bias, pb.residual = residual, pb.out = out;
+    pb.out_str[0] = Cout, pb.out_str[1] = (int64_t)W * Cout, pb.out_str[2] = (int64_t)H * W * Cout;
+    for (int i = 0; i < 3; ++i) pb.res_str[i] = pb.out_str[i];
+    pb.variant = variant;
+    return gemm::run(pb, (cudaStream_t)stream);
+}
+
+extern "C" int mvoc_temporal_conv3(const void* x, const void* w_taps, const void* bias, const void* residual, void* out,
+                                   int B, int T, int64_t S, int Cin, int Cout, int dtype, int variant, void* stream) {
+    gemm::Problem pb{};
+    pb.what = "mvoc_temporal_conv3";
+    MVOC_REQUIRE(B > 0 && T > 0 && S > 0 && Cin > 0 && Cout > 0, MVOC_ERR_INVALID_ARG,
+                 "%s: empty problem B=%d T=%d S=%lld Cin=%d Cout=%d", pb.what, B, T, (long long)S, Cin, Cout);
+    pb.dtype = dtype;
+    pb.d1 = S, pb.d2 = T, pb.d3 = B;
+    pb.n_src = 1;
+    gemm::Source& s0 = pb.src[0];
+    s0.a = x, s0.K = Cin, s0.w = w_taps, s0.taps = 3;
+    s0.a_str[0] = Cin, s0.a_str[1] = S * Cin, s0.a_str[2] = (int64_t)T * S * Cin;
+    for (int t = 0; t < 3; ++t) s0.off[t][0] = 0, s0.off[t][1] = (int8_t)(t - 1), s0.off[t][2] = 0;
+    pb.N = Cout, pb.w_rows = Cout;
+    pb.bias = bias, pb.residual = residual, pb.out = out;
+    pb.out_str[0] = Cout, pb.out_str[1] = S * Cout, pb.out_str[2] = (int64_t)T * S * Cout;
+    for (int i = 0; i < 3; ++i) pb.res_str[i] = pb.out_str[i];
+    pb.variant = variant;
+    return gemm::run(pb, (cudaStream_t)stream);
+}
+
+extern "C" int mvoc_linear(const void* x, const void* w, const void* bias, const void* residual, void* out, int64_t M,
+                           int K, int N, int64_t ldx, int64_t ldr, int64_t ldo, int dtype, int variant, void* stream) {
+    gemm::Problem pb{};
+    pb.what = "mvoc_linear";
+    MVOC_REQUIRE(M > 0 && K > 0 && N > 0, MVOC_ERR_INVALID_ARG, "%s: empty problem M=%lld K=%d N=%d", pb.what,
+                 (long long)M, K, N);
+    MVOC_REQUIRE(ldx >= K && ldo >= N && (residual == nullptr || ldr >= N), MVOC_ERR_INVALID_ARG,
+                 "%s: leading dimensions ldx=%lld ldr=%lld ldo=%lld too small for K=%d N=%d", pb.what, (long long)ldx,
+                 (long long)ldr, (long long)ldo, K, N);
+    pb.dtype = dtype;
+    pb.d1 = M, pb.d2 = 1, pb.d3 = 1;
+    pb.n_src = 1;
+    gemm::Source& s0 = pb.src[0];
+    s0.a = x, s0.K = K, s0.w = w, s0.taps = 1;
+    s0.a_str[0] = ldx, s0.a_str[1] = 0, s0.a_str[2] = 0;
+    s0.off[0][0] = s0.off[0][1] = s0.off[0][2] = 0;
+    pb.N = N, pb.w_rows = N;
+    pb.bias = bias, pb.residual = residual, pb.out = out;
+    pb.out_str[0] = ldo, pb.out_str[1] = 0, pb.out_str[2] = 0;
+    pb.res_str[0] = ldr, pb.res_str[1] = 0, pb.res_str[2] = 0;
+    pb.variant = variant;
+    return gemm::run(pb, (cudaStream_t)stream);
+}
+
+extern "C" int mvoc_linear_geglu(const void* x, const void* w, const void* bias, void* out, int64_t M, int K, int F,
+                                 int dtype, int variant, void* stream) {
+    gemm::Problem pb{};
+    pb.what = "mvoc_linear_geglu";
+    MVOC_REQUIRE(M > 0 && K > 0 && F > 0, MVOC_ERR_INVALID_ARG, "%s: empty problem M=%lld K=%d F=%d", pb.what,
+                 (long long)M, K, F);
+    pb.dtype = dtype;
+    pb.d1 = M, pb.d2 = 1, pb.d3 = 1;
+    pb.n_src = 1;
+    gemm::Source& s0 = pb.src[0];
+    s0.a = x, s0.K = K, s0.w = w, s0.taps = 1;
+    s0.a_str[0] = K, s0.a_str[1] = 0, s0.a_str[2] = 0;
+    s0.off[0][0] = s0.off[0][1] = s0.off[0][2] = 0;
+    pb.N = F, pb.w_rows = 2 * (int64_t)F;
+    pb.bias = bias, pb.residual = nullptr, pb.out = out;
+    pb.out_str[0] = F, pb.out_str[1] = 0, pb.out_str[2] = 0;
+    pb.geglu = 1;
+    pb.variant = variant;
+    return gemm::run(pb, (cudaStream_t)stream);
+}

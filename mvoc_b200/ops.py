@@ -82,10 +82,23 @@ def _dt(t: torch.Tensor) -> int:
 
 
 def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    """Every tensor must live on the CURRENT CUDA device: the C-ABI launches on the current device and on its
+    current stream, so a tensor of another GPU would be an illegal address there.  (One process per GPU is the
+    deployment model; scripts call torch.cuda.set_device before touching the pipeline.)"""
+    cur = -1
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError(
                 "mvoc_b200 ops run on CUDA tensors only (sm_100a kernels; there is no CPU fallback)"
+            )
+        if cur < 0:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise RuntimeError(
+                f"mvoc_b200 ops launch on the current CUDA device (cuda:{cur}) but got a tensor on {t.device}; "
+                "call torch.cuda.set_device(device) first (one process per GPU)"
             )
 
 
@@ -522,5 +535,149 @@ def temporal_attention_frames(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
         rc = _cabi.load().mvoc_attn_temporal_strided_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
                                                         B, S, T, heads, HEAD_DIM, arr, float(scale), _dt(q), _stream())
     _cabi.check(rc, "mvoc_attn_temporal_strided_fwd")
+    _count()
+    return out
+
+
+# --------------------------------------------------------------------------
+# dense work on tcgen05 tensor cores (csrc/gemm_tc.cu): convolutions, temporal convolutions, Linears
+# --------------------------------------------------------------------------
+# bit 0 = CTA pairs (tcgen05 cta_group::2); bits 8.. = tile-width override.  An experiment switch for A/B
+# measurements (bench.py records it); the default is the configuration the product numbers were measured with.
+GEMM_VARIANT = int(os.environ.get("MVOC_GEMM_VARIANT", "0") or 0)
+
+
+def _rows(t: torch.Tensor, what: str):
+    """(rows, row stride in elements) of a tensor whose leading dims collapse into uniformly strided rows."""
+    if t.dim() < 2 or t.stride(-1) != 1:
+        raise ValueError(f"{what}: need [..., C] with a contiguous last dim, got {tuple(t.shape)} strides {t.stride()}")
+    ld = t.stride(-2)
+    rows = t.shape[-2]
+    for i in range(t.dim() - 3, -1, -1):
+        if t.shape[i] != 1 and t.stride(i) != t.stride(i + 1) * t.shape[i + 1]:
+            raise ValueError(f"{what}: leading dims of {tuple(t.shape)} (strides {t.stride()}) do not collapse into rows")
+        rows *= t.shape[i]
+    return rows, ld
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+           variant: Optional[int] = None) -> torch.Tensor:
+    """out[..., N] = x[..., K] @ weight[N, K]^T (+ bias) (+ residual) in one tcgen05 kernel (mvoc_linear)."""
+    _need_cuda(x, weight, bias, residual, out)
+    N, K = weight.shape
+    if x.shape[-1] != K or not weight.is_contiguous():
+        raise ValueError(f"linear: x {tuple(x.shape)} vs contiguous weight {tuple(weight.shape)}")
+    M, ldx = _rows(x, "linear x")
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (N,), dtype=x.dtype, device=x.device)
+    Mo, ldo = _rows(out, "linear out")
+    ldr = 0
+    if residual is not None:
+        Mr, ldr = _rows(residual, "linear residual")
+        if Mr != M or residual.shape[-1] != N:
+            raise ValueError(f"linear: residual {tuple(residual.shape)} does not match [{M}, {N}]")
+    if Mo != M or out.shape[-1] != N:
+        raise ValueError(f"linear: out {tuple(out.shape)} does not match [{M}, {N}]")
+    v = GEMM_VARIANT if variant is None else variant
+    with _Timed(("gemm", "linear", M, K, N), 2.0 * M * K * N):
+        rc = _cabi.load().mvoc_linear(x.data_ptr(), weight.data_ptr(), _ptr(bias), _ptr(residual), out.data_ptr(),
+                                      M, K, N, ldx, ldr, ldo, _dt(x), int(v), _stream())
+    _cabi.check(rc, "mvoc_linear")
+    _count()
+    return out
+
+
+def linear_geglu(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None, variant: Optional[int] = None) -> torch.Tensor:
+    """GEGLU projection with the gate in the GEMM epilogue: x [..., K], weight [2F, K] -> [..., F]."""
+    _need_cuda(x, weight, bias, out)
+    F2, K = weight.shape
+    F = F2 // 2
+    if x.shape[-1] != K or not x.is_contiguous() or not weight.is_contiguous():
+        raise ValueError(f"linear_geglu: contiguous x {tuple(x.shape)} vs weight {tuple(weight.shape)}")
+    M = x.numel() // K
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (F,), dtype=x.dtype, device=x.device)
+    v = GEMM_VARIANT if variant is None else variant
+    with _Timed(("gemm", "geglu", M, K, F2), 2.0 * M * K * F2):
+        rc = _cabi.load().mvoc_linear_geglu(x.data_ptr(), weight.data_ptr(), _ptr(bias), out.data_ptr(), M, K, F,
+                                            _dt(x), int(v), _stream())
+    _cabi.check(rc, "mvoc_linear_geglu")
+    _count()
+    return out
+
+
+def conv_taps(weight: torch.Tensor) -> torch.Tensor:
+    """Conv2d weight [Cout, Cin, 3, 3] -> tap-major K-major [9, Cout, Cin]; Conv3d weight [Cout, Cin, 3, 1, 1] ->
+    [3, Cout, Cin] (the operand layout of mvoc_conv3x3_nhwc / mvoc_temporal_conv3)."""
+    if weight.dim() == 5:
+        co, ci, kt, kh, kw = weight.shape
+        if (kt, kh, kw) != (3, 1, 1):
+            raise ValueError("conv_taps: Conv3d kernels must be (3, 1, 1)")
+        return weight.reshape(co, ci, 3).permute(2, 0, 1).contiguous()
+    co, ci, kh, kw = weight.shape
+    if (kh, kw) != (3, 3):
+        raise ValueError("conv_taps: Conv2d kernels must be 3x3")
+    return weight.permute(2, 3, 0, 1).reshape(9, co, ci).contiguous()
+
+
+def conv3x3(x: torch.Tensor, w_taps: torch.Tensor, bias: Optional[torch.Tensor] = None,
+            residual: Optional[torch.Tensor] = None, x2: Optional[torch.Tensor] = None,
+            w2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+            variant: Optional[int] = None) -> torch.Tensor:
+    """3x3 / stride 1 / pad 1 convolution on channels-last x [N, H, W, Cin] with w_taps [9, Cout, Cin]
+    (+ bias) (+ x2 [N, H, W, Cin2] @ w2 [Cout, Cin2]^T, the 1x1 shortcut) (+ residual [N, H, W, Cout])."""
+    _need_cuda(x, w_taps, bias, residual, x2, w2, out)
+    if x.dim() != 4 or not x.is_contiguous():
+        raise ValueError(f"conv3x3: need contiguous [N, H, W, Cin], got {tuple(x.shape)}")
+    N, H, W, ci = x.shape
+    if w_taps.dim() != 3 or w_taps.shape[0] != 9 or w_taps.shape[2] != ci or not w_taps.is_contiguous():
+        raise ValueError(f"conv3x3: w_taps must be contiguous [9, Cout, {ci}], got {tuple(w_taps.shape)}")
+    co = w_taps.shape[1]
+    ci2 = 0
+    if (x2 is None) != (w2 is None):
+        raise ValueError("conv3x3: x2 and w2 go together")
+    if x2 is not None:
+        ci2 = x2.shape[-1]
+        if tuple(x2.shape) != (N, H, W, ci2) or not x2.is_contiguous() or tuple(w2.shape) != (co, ci2) \
+                or not w2.is_contiguous():
+            raise ValueError("conv3x3: x2 must be contiguous [N, H, W, Cin2] and w2 contiguous [Cout, Cin2]")
+    if out is None:
+        out = torch.empty((N, H, W, co), dtype=x.dtype, device=x.device)
+    for t, nm in ((out, "out"), (residual, "residual")):
+        if t is not None and (tuple(t.shape) != (N, H, W, co) or not t.is_contiguous()):
+            raise ValueError(f"conv3x3: {nm} must be contiguous [{N}, {H}, {W}, {co}]")
+    v = GEMM_VARIANT if variant is None else variant
+    with _Timed(("gemm", "conv3x3", N * H * W, 9 * ci + ci2, co), 2.0 * N * H * W * co * (9 * ci + ci2)):
+        rc = _cabi.load().mvoc_conv3x3_nhwc(x.data_ptr(), w_taps.data_ptr(), _ptr(bias), _ptr(residual), _ptr(x2),
+                                            _ptr(w2), ci2, out.data_ptr(), N, H, W, ci, co, _dt(x), int(v), _stream())
+    _cabi.check(rc, "mvoc_conv3x3_nhwc")
+    _count()
+    return out
+
+
+def temporal_conv3(x: torch.Tensor, w_taps: torch.Tensor, bias: Optional[torch.Tensor], videos: int, frames: int,
+                   residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                   variant: Optional[int] = None) -> torch.Tensor:
+    """Conv3d (3,1,1) over the frames of frame-major channels-last rows: x [(b t), ..., Cin] -> [(b t), ..., Cout]."""
+    _need_cuda(x, w_taps, bias, residual, out)
+    if not x.is_contiguous() or x.shape[0] != videos * frames:
+        raise ValueError(f"temporal_conv3: need contiguous [{videos}*{frames}, ..., Cin], got {tuple(x.shape)}")
+    ci = x.shape[-1]
+    if w_taps.dim() != 3 or w_taps.shape[0] != 3 or w_taps.shape[2] != ci or not w_taps.is_contiguous():
+        raise ValueError(f"temporal_conv3: w_taps must be contiguous [3, Cout, {ci}], got {tuple(w_taps.shape)}")
+    co = w_taps.shape[1]
+    S = x.numel() // (videos * frames * ci)
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (co,), dtype=x.dtype, device=x.device)
+    for t, nm in ((out, "out"), (residual, "residual")):
+        if t is not None and (t.numel() != videos * frames * S * co or not t.is_contiguous()):
+            raise ValueError(f"temporal_conv3: {nm} must be contiguous with {videos * frames * S} rows of {co}")
+    v = GEMM_VARIANT if variant is None else variant
+    with _Timed(("gemm", "tconv3", videos * frames * S, 3 * ci, co), 2.0 * videos * frames * S * co * 3 * ci):
+        rc = _cabi.load().mvoc_temporal_conv3(x.data_ptr(), w_taps.data_ptr(), _ptr(bias), _ptr(residual),
+                                              out.data_ptr(), videos, frames, S, ci, co, _dt(x), int(v), _stream())
+    _cabi.check(rc, "mvoc_temporal_conv3")
     _count()
     return out

@@ -34,9 +34,15 @@ def ddim_latents_filename(t: int) -> str:
     return f"ddim_latents_{int(t)}.pt"
 
 
-def save_ddim_latents_at_t(latents: torch.Tensor, t: int, path: str) -> None:
+def save_ddim_latents_at_t(latents: torch.Tensor, t: int, path: str, dtype=torch.float16) -> None:
+    """One `ddim_latents_{t}.pt` in the reference's wire dtype: it saves its fp16 pipeline latents
+    (pipeline_i2vgen_xl.py:1990-1993) and reads them back with `.to(device)`, which keeps the dtype — an fp32
+    file would meet fp16 weights there.  `dtype=None` keeps the tensor's own dtype (our packed store stays fp32)."""
     os.makedirs(path, exist_ok=True)
-    torch.save(latents.detach().clone().cpu(), os.path.join(path, ddim_latents_filename(t)))
+    x = latents.detach().clone().cpu()
+    if dtype is not None:
+        x = x.to(dtype)
+    torch.save(x, os.path.join(path, ddim_latents_filename(t)))
 
 
 def load_ddim_latents_at_t(t, ddim_latents_path: str) -> torch.Tensor:
@@ -164,8 +170,9 @@ class I2VGenXLPipeline:
         # the capture bakes in control flow (which hooks fire) and addresses (input buffer, conditioning cache,
         # token masks): all of them are part of the key
         mask = getattr(unet.conv_out, "mask", None)
-        mask_id = tuple((m[0].data_ptr(), m[1].data_ptr()) for m in mask) if mask else ()
-        key = (pnp_utils.hook_signature(unet), tuple(sample.shape), id(cond), par.world, mask_id)
+        mask_handle = pnp_utils._MASKS.handle(mask) if mask else None
+        key = (pnp_utils.hook_signature(unet), tuple(sample.shape), id(cond), par.world,
+               mask_handle.serial if mask_handle is not None else 0, unet.__dict__.get("derived_epoch", 0))
         entry = self._graphs.get(key)
         if entry is None:
             # eager warm-up on a side stream (lazy weight fusions, cuDNN autotune, mask caches), then capture
@@ -185,7 +192,7 @@ class I2VGenXLPipeline:
                     out = self._unet_body(sample, cond, cache, (f0, f1))
             finally:
                 ops.set_timer(timer)
-            entry = (graph, out)
+            entry = (graph, out, mask_handle, cond)   # the handle / cond keep the captured addresses alive
             self._graphs[key] = entry
         entry[0].replay()
         return entry[1]
@@ -295,6 +302,7 @@ class I2VGenXLPipeline:
         output_dir: Optional[str] = None,
         max_steps: Optional[int] = None,
         keep: bool = True,
+        save_dtype=torch.float16,
     ) -> Dict[int, torch.Tensor]:
         """DDIM inversion loop, pipeline_i2vgen_xl.py:1914-2003 (guidance 1.0 => batch 1, :517).
         Returns {t: latents at level t}; with output_dir also writes ddim_latents_{t}.pt (:1988-1993)."""
@@ -314,7 +322,7 @@ class I2VGenXLPipeline:
             if keep:
                 saved[t] = x.clone()                                            # :1986
             if output_dir is not None:
-                save_ddim_latents_at_t(x, t, output_dir)                        # :1988-1993
+                save_ddim_latents_at_t(x, t, output_dir, save_dtype)            # :1988-1993
         return saved
 
 
@@ -331,6 +339,8 @@ def init_pnp(pipe: I2VGenXLPipeline, scheduler: DDIMSchedule, config) -> dict:
     conv_ts = ts[:conv_t] if conv_t >= 0 else []
     spa_ts = ts[:spa_t] if spa_t >= 0 else []
     tmp_ts = ts[:tmp_t] if tmp_t >= 0 else []
+    pnp_utils._MASKS.clear()       # a new run: drop the token masks (and graphs keyed on them) of the previous one
+    pipe._graphs.clear()
     pnp_utils.modify_diffuser_attention_forward(pipe.unet)
     pnp_utils.register_temp_attention_pnp(pipe, tmp_ts, config.inject_background)
     pnp_utils.register_spatial_attention_pnp(pipe, spa_ts, config.inject_background)

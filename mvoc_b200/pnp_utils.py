@@ -26,7 +26,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .unet3d import AttnProcessor2_0, run_attention
+from .unet3d import AttnProcessor2_0, dense_linear, run_attention
 
 MaskPair = Tuple[torch.Tensor, torch.Tensor]
 
@@ -38,21 +38,64 @@ class _MaskCache:
     """The reference re-materialises a [T,h,w,C] mask per object per layer per step
     (pnp_utils.py:648-656, :805-809).  The kernels read one value per token, so the nearest-resized,
     token-ordered masks are built once per (mask list, resolution, kind, shard) and reused.
-    Token order is (frame, pixel) everywhere — the row order of the channels-last activations."""
+    Token order is (frame, pixel) everywhere — the row order of the channels-last activations.
+
+    Entries are found by the IDENTITY of the mask tensors (and their in-place version counters) and hold
+    strong references to them, so an address recycled by the allocator can never alias a dead entry; every
+    entry carries a serial number that CUDA-graph keys use (mvoc_b200.pipeline).  The store is a small LRU
+    and is emptied by init_pnp."""
+
+    MAX_ENTRIES = 8
+
+    class _Entry:
+        __slots__ = ("tensors", "versions", "serial", "derived")
+
+        def __init__(self, tensors, serial):
+            self.tensors = tensors
+            self.versions = tuple(t._version for t in tensors)
+            self.serial = serial
+            self.derived = {}
+
+        def matches(self, tensors) -> bool:
+            return (len(tensors) == len(self.tensors)
+                    and all(a is b for a, b in zip(tensors, self.tensors))
+                    and all(t._version == v for t, v in zip(tensors, self.versions)))
 
     def __init__(self):
-        self._store = {}
+        self._entries = []
+        self._serial = 0
 
-    @staticmethod
-    def _key(mask: Sequence[MaskPair], *extra):
-        return extra + tuple((m[0].data_ptr(), m[1].data_ptr(), m[0]._version, m[1]._version) for m in mask)
+    def clear(self) -> None:
+        self._entries.clear()
+
+    def __len__(self) -> int:
+        return len(self._entries)
+
+    def _entry(self, mask: Sequence[MaskPair]) -> "_MaskCache._Entry":
+        tensors = tuple(t for pair in mask for t in (pair[0], pair[1]))
+        for i, e in enumerate(self._entries):
+            if e.matches(tensors):
+                if i:
+                    self._entries.insert(0, self._entries.pop(i))
+                return e
+        self._serial += 1
+        e = self._Entry(tensors, self._serial)
+        self._entries.insert(0, e)
+        del self._entries[self.MAX_ENTRIES:]
+        return e
+
+    def handle(self, mask: Sequence[MaskPair]) -> "_MaskCache._Entry":
+        """The cache entry of a mask list.  Captured CUDA graphs bake in the addresses of the derived token
+        masks: they key on `handle.serial` and keep the handle alive so that an LRU eviction cannot free them."""
+        return self._entry(mask)
 
     def tokens(self, mask, h, w, soft: bool, frames=None, pixels=None) -> torch.Tensor:
         """[n_obj, T'*S'] in (frame, pixel) order.  soft=False: uint8 from the BINARY masks
         (pnp_utils.py:648-651, :986-994); soft=True: float32 from the FLOAT masks (:805-809).  Both are
         nearest-resized from the latent resolution to (h, w); `frames` / `pixels` = (lo, hi) shard ranges."""
-        key = self._key(mask, "soft" if soft else "bin", h, w, frames, pixels)
-        out = self._store.get(key)
+        store = self._entry(mask).derived
+        key = ("soft" if soft else "bin", h, w, frames, pixels)
+        out = store.get(key)
         if out is None:
             rows = []
             for mf, mb in mask:
@@ -65,19 +108,20 @@ class _MaskCache:
                     m = m[:, pixels[0]:pixels[1]]
                 rows.append(m.reshape(-1) if soft else (m != 0).to(torch.uint8).reshape(-1))
             out = torch.stack(rows).contiguous()
-            self._store[key] = out
+            store[key] = out
         return out
 
     def feature_planes(self, mask, frames=None) -> torch.Tensor:
         """[n_obj, T', H*W] uint8 from the BINARY masks at full latent resolution (pnp_utils.py:986-994)."""
-        key = self._key(mask, "feat", frames)
-        out = self._store.get(key)
+        store = self._entry(mask).derived
+        key = ("feat", frames)
+        out = store.get(key)
         if out is None:
             planes = [mb[0, 0].reshape(mb.shape[2], -1).to(torch.uint8) for _, mb in mask]
             if frames is not None:
                 planes = [p_[frames[0]:frames[1]] for p_ in planes]
             out = torch.stack(planes).contiguous()
-            self._store[key] = out
+            store[key] = out
         return out
 
 
@@ -123,9 +167,9 @@ class _InjectingProcessor(AttnProcessor2_0):
         if hidden_states.shape[0] % nb != 0:
             raise ValueError(f"batch {hidden_states.shape[0]} is not divisible into n_obj+3={nb} branches")
         # separate projections: the blend kernel wants slot-major contiguous Q and K
-        q = attn.to_q(hidden_states)                                            # :604
-        k = attn.to_k(hidden_states)                                            # :611
-        v = attn.to_v(hidden_states)                                            # :612
+        q = dense_linear(hidden_states, attn.to_q.weight)                       # :604
+        k = dense_linear(hidden_states, attn.to_k.weight)                       # :611
+        v = dense_linear(hidden_states, attn.to_v.weight)                       # :612
         par = _partition(attn)
         n_frames_total = mask[0][0].shape[2]
         if self.temporal:
@@ -139,7 +183,7 @@ class _InjectingProcessor(AttnProcessor2_0):
             tokens = _MASKS.tokens(mask, height, width, soft=False, frames=frm)  # binary mask (:648)
         ops.qk_blend_(q, k, tokens, n_obj, bool(self.inject_background))         # :628-672 / :782-850
         out = run_attention(q, k, v, attn.heads, attn.temporal)                  # :684 / :862
-        return attn.to_out[0](out)                                              # :692
+        return attn.out_proj(out)                                               # :692 (+ the block's skip add)
 
 
 def register_spatial_attention_pnp(model, injection_schedule, inject_background=False):

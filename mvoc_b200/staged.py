@@ -16,8 +16,6 @@ from . import _cabi
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libmvoc_b200_staged.so")
 
 SIGNATURES = {
-    "mvoc_conv3x3_nhwc": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
-    "mvoc_linear_geglu": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_void_p]),
     "mvoc_attn_fwd_split": (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_int64] * 12 + [c_float, c_int, c_int, c_void_p]),
 }
 
@@ -50,52 +48,6 @@ def _need(*ts) -> None:
     for t in ts:
         if t is not None and (not t.is_cuda or t.dtype != torch.bfloat16 or not t.is_contiguous()):
             raise ValueError("staged kernels take contiguous bf16 CUDA tensors (no fallback)")
-
-
-def prepare_conv_weight(weight: torch.Tensor) -> torch.Tensor:
-    """torch Conv2d weight [Cout, Cin, 3, 3] -> tap-major [9, Cout, Cin] (tap = kh*3 + kw), contiguous."""
-    co, ci, kh, kw = weight.shape
-    if (kh, kw) != (3, 3):
-        raise ValueError("3x3 kernels only")
-    return weight.permute(2, 3, 0, 1).reshape(9, co, ci).contiguous()
-
-
-def conv3x3_nhwc(x: torch.Tensor, w_taps: torch.Tensor, bias: Optional[torch.Tensor] = None,
-                 residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-                 variant: int = 0) -> torch.Tensor:
-    """x [N, H, W, Cin], w_taps [9, Cout, Cin] -> [N, H, W, Cout] (+ bias, + residual), stride 1, padding 1."""
-    _need(x, w_taps, bias, residual, out)
-    N, H, W, ci = x.shape
-    if w_taps.dim() != 3 or w_taps.shape[0] != 9 or w_taps.shape[2] != ci:
-        raise ValueError(f"w_taps must be [9, Cout, {ci}], got {tuple(w_taps.shape)}")
-    co = w_taps.shape[1]
-    if out is None:
-        out = torch.empty((N, H, W, co), dtype=x.dtype, device=x.device)
-    if residual is not None and residual.shape != out.shape:
-        raise ValueError("residual must have the shape of the output")
-    p = lambda t: None if t is None else t.data_ptr()
-    rc = load().mvoc_conv3x3_nhwc(x.data_ptr(), w_taps.data_ptr(), p(bias), p(residual), out.data_ptr(), N, H, W, ci,
-                                  co, _cabi.MVOC_BF16, int(variant), torch.cuda.current_stream().cuda_stream)
-    _check(rc, "mvoc_conv3x3_nhwc")
-    return out
-
-
-def linear_geglu(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
-                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x [..., K], weight [2F, K] (torch Linear) -> value * gelu(gate), [..., F]."""
-    _need(x, weight, bias, out)
-    K = x.shape[-1]
-    M = x.numel() // K
-    F2 = weight.shape[0]
-    if weight.shape[1] != K or F2 % 2:
-        raise ValueError(f"weight must be [2F, {K}], got {tuple(weight.shape)}")
-    F = F2 // 2
-    if out is None:
-        out = torch.empty(x.shape[:-1] + (F,), dtype=x.dtype, device=x.device)
-    rc = load().mvoc_linear_geglu(x.data_ptr(), weight.data_ptr(), None if bias is None else bias.data_ptr(),
-                                  out.data_ptr(), M, K, F, _cabi.MVOC_BF16, torch.cuda.current_stream().cuda_stream)
-    _check(rc, "mvoc_linear_geglu")
-    return out
 
 
 def attention_split(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None,

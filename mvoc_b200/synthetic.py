@@ -49,6 +49,9 @@ WORKLOADS: Dict[str, Workload] = {
     "config2": Workload("config2", "full", 16, 64, 64, 2),
     # configs[4]: 32 x 88x160 (704x1280 px), bg + 3 objects
     "config5": Workload("config5", "full", 32, 88, 160, 3),
+    # the benchmarked model and latent size with 2 of the 16 frames: full-architecture GPU parity against the
+    # fp32 CPU oracle at a cost the oracle can pay (one step ~10 s on 16 host cores)
+    "config2_t2": Workload("config2_t2", "full", 2, 64, 64, 2),
     # small full-architecture case for GPU parity tests
     "full_small": Workload("full_small", "full", 8, 32, 32, 2),
     "reduced2": Workload("reduced2", "reduced", 8, 32, 32, 2),

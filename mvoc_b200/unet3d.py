@@ -7,8 +7,12 @@ checkpoint's state dict loads unchanged.
 
 What runs underneath is this repo's C-ABI library (``mvoc_b200.ops``): every attention
 (tcgen05 flash attention / warp-per-pixel temporal attention), every GroupNorm(+SiLU), the GEGLU
-gate, the mask blends and the latent/DDIM updates are sm_100a kernels.  Dense GEMMs / convolutions
-stay on cuBLAS / cuDNN through torch.  There is no CPU path: tensors must be CUDA.
+gate, the mask blends and the latent/DDIM updates are sm_100a kernels, and so is the dense work (SURVEY §2.2 K9,
+§8f-1): 3x3 convolutions, temporal convolutions and every Linear / 1x1 conv with 64-aligned channel counts run on
+the tcgen05 implicit-GEMM kernel (csrc/gemm_tc.cu) with bias / residual / GEGLU / shortcut-conv fused into its
+epilogue.  What stays on cuDNN / cuBLAS through torch: conv_in (8 input channels), conv_out (4 output channels),
+the three stride-2 downsamplers, the time / fps embeddings (M <= 80 rows) and the once-per-run conditioning stem.
+There is no CPU path: tensors must be CUDA.
 
 Data layout: activations are channels-last ``[B*T, H, W, C]`` (frames outermost) from conv_in to
 conv_out.  In that layout every 1x1 conv / Linear / LayerNorm is a row-wise op on ``[B*T*H*W, C]``,
@@ -84,40 +88,72 @@ class _Ctx:
         self.full_hw = None    # (h, w) of the un-sharded frame while a temporal operator runs on pixel shards
 
 
-# MVOC_STAGED=1 routes the stride-1 3x3 convolutions and the GEGLU projection through the tcgen05 kernels staged
-# in libmvoc_b200_staged.so (include/mvoc_b200_staged.h).  Off by default: those kernels have not been validated
-# on hardware yet, the measured product path is cuDNN / cuBLAS + mvoc_geglu.
-_STAGED = os.environ.get("MVOC_STAGED") == "1"
+# MVOC_DENSE=lib sends the dense work to cuDNN / cuBLAS instead of this repo's tcgen05 kernels: the A/B baseline
+# of bench.py (recorded in its `switches`), never the product configuration.
+_DENSE_TC = os.environ.get("MVOC_DENSE", "tc") != "lib"
+_TC_DTYPES = (torch.bfloat16, torch.float16)
 
 
-def _staged_conv_ok(conv: nn.Conv2d) -> bool:
-    return (conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1)
-            and conv.dilation == (1, 1) and conv.groups == 1 and conv.in_channels % 64 == 0
-            and conv.out_channels % 64 == 0)
+def derived(module: nn.Module, name: str, sources, build):
+    """Weight re-layouts (tap-major conv filters, fused QKV, ...) cached on the module and rebuilt when a source
+    parameter is replaced, moved, cast or edited in place (load_state_dict copies in place and bumps _version)."""
+    store = module.__dict__.setdefault("_derived", {})
+    key = tuple((p.data_ptr(), p._version) for p in sources)
+    hit = store.get(name)
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            hit = (key, build())
+        store[name] = hit
+    return hit[1]
 
 
-def _staged_conv(x, conv, bias=None, residual=None):
-    from . import staged
+def invalidate_derived(root: nn.Module) -> None:
+    """Drop every cached weight re-layout under `root` (load_state_dict post-hook; captured CUDA graphs that
+    baked their addresses in are dropped by the pipeline through `derived_epoch`)."""
+    for m in root.modules():
+        m.__dict__.pop("_derived", None)
+    root.__dict__["derived_epoch"] = root.__dict__.get("derived_epoch", 0) + 1
 
-    wt = conv.__dict__.get("_w_taps")
-    if wt is None or wt.device != x.device or wt.dtype != x.dtype:
-        wt = staged.prepare_conv_weight(conv.weight.detach()).to(x.dtype)
-        conv.__dict__["_w_taps"] = wt
-    return staged.conv3x3_nhwc(x, wt, conv.bias if bias is None else bias, residual)
+
+def _tc_ok(x: torch.Tensor, k: int, n: int) -> bool:
+    return _DENSE_TC and x.is_cuda and x.dtype in _TC_DTYPES and k % 64 == 0 and n % 64 == 0
+
+
+def dense_linear(x, weight, bias=None, residual=None):
+    """x [..., K] @ weight[N, K]^T (+ bias) (+ residual): mvoc_linear, bias and residual in the epilogue."""
+    n, k = weight.shape[0], weight.shape[1]
+    if _tc_ok(x, k, n):
+        return ops.linear(x, weight, bias, residual)
+    y = F.linear(x, weight, bias)
+    return y if residual is None else y.add_(residual)
 
 
 def conv_nhwc(x: torch.Tensor, conv: nn.Conv2d, bias: Optional[torch.Tensor] = None,
-              residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """3x3 / strided conv on a channels-last activation [N, H, W, C] -> [N, H', W', C'] (cuDNN NHWC kernels:
-    the permuted view IS torch's channels_last memory format, so no nchw<->nhwc conversion runs).
-    `residual` (same shape as the result) is added to it."""
-    if _STAGED and _staged_conv_ok(conv):
-        return _staged_conv(x, conv, bias, residual)
-    if residual is not None:
-        return conv_nhwc(x, conv, bias).add_(residual)
-    y = F.conv2d(x.permute(0, 3, 1, 2), conv.weight, conv.bias if bias is None else bias, conv.stride, conv.padding)
-    y = y.permute(0, 2, 3, 1)
-    return y if y.is_contiguous() else y.contiguous()
+              residual: Optional[torch.Tensor] = None, shortcut=None) -> torch.Tensor:
+    """Conv2d on a channels-last activation [N, H, W, C] -> [N, H', W', C'].  `residual` (shaped like the result)
+    is added to it; `shortcut` = (x2 [N, H, W, C2], conv1x1) accumulates the resnet's 1x1 shortcut conv of x2 into
+    the same output tile (its bias must already be folded into `bias`).
+    3x3 / stride 1 / pad 1 with 64-aligned channels: mvoc_conv3x3_nhwc (implicit GEMM on tcgen05).  Anything else
+    (conv_in, conv_out, the stride-2 downsamplers): cuDNN NHWC kernels on the permuted view, which IS torch's
+    channels_last memory format, so no nchw<->nhwc conversion runs."""
+    b = conv.bias if bias is None else bias
+    if (conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1)
+            and conv.groups == 1 and _tc_ok(x, conv.in_channels, conv.out_channels)
+            and (shortcut is None or shortcut[1].in_channels % 64 == 0)):
+        wt = derived(conv, "w_taps", (conv.weight,), lambda: ops.conv_taps(conv.weight))
+        x2 = w2 = None
+        if shortcut is not None:
+            x2, sc = shortcut
+            w2 = derived(sc, "w_rows", (sc.weight,),
+                         lambda: sc.weight.reshape(sc.out_channels, sc.in_channels).contiguous())
+        return ops.conv3x3(x if x.is_contiguous() else x.contiguous(), wt, b, residual, x2, w2)
+    y = F.conv2d(x.permute(0, 3, 1, 2), conv.weight, b, conv.stride, conv.padding).permute(0, 2, 3, 1)
+    y = y if y.is_contiguous() else y.contiguous()
+    if shortcut is not None:
+        x2, sc = shortcut
+        co, c2 = sc.out_channels, sc.in_channels
+        y.view(-1, co).addmm_(x2.reshape(-1, c2), sc.weight.view(co, c2).t())
+    return y if residual is None else y.add_(residual)
 
 
 class GroupNormAct(nn.GroupNorm):
@@ -186,10 +222,10 @@ class AttnProcessor2_0:
         if encoder_hidden_states is None:
             q, k, v = attn.qkv_self(hidden_states)
         else:
-            q = attn.to_q(hidden_states)
+            q = dense_linear(hidden_states, attn.to_q.weight)
             k, v = attn.kv_cross(encoder_hidden_states)
         out = run_attention(q, k, v, attn.heads, attn.temporal if encoder_hidden_states is None else None)
-        return attn.to_out[0](out)
+        return attn.out_proj(out)
 
 
 class Attention(nn.Module):
@@ -211,8 +247,7 @@ class Attention(nn.Module):
         self.to_out = nn.ModuleList([nn.Linear(self.inner_dim, query_dim, bias=out_bias), nn.Dropout(0.0)])
         self._processor = None
         self._accepts_hw = False
-        self._w_qkv = None
-        self._w_kv = None
+        self._residual = None        # offered by the transformer block, consumed by out_proj
         self.temporal: Optional[TemporalShape] = None   # set per call by the temporal transformer
         self.ctx: Optional[_Ctx] = None
         self.processor = AttnProcessor2_0()
@@ -231,18 +266,24 @@ class Attention(nn.Module):
 
     def qkv_self(self, x):
         """One GEMM for the three self-attention projections; q, k, v are strided views."""
-        if self._w_qkv is None or self._w_qkv.device != x.device or self._w_qkv.dtype != x.dtype:
-            self._w_qkv = torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight], dim=0).contiguous()
-        qkv = F.linear(x, self._w_qkv)
+        ws = (self.to_q.weight, self.to_k.weight, self.to_v.weight)
+        w = derived(self, "w_qkv", ws, lambda: torch.cat(ws, dim=0).contiguous())
+        qkv = dense_linear(x, w)
         c = self.inner_dim
         return qkv[..., :c], qkv[..., c:2 * c], qkv[..., 2 * c:]
 
     def kv_cross(self, ctx):
-        if self._w_kv is None or self._w_kv.device != ctx.device or self._w_kv.dtype != ctx.dtype:
-            self._w_kv = torch.cat([self.to_k.weight, self.to_v.weight], dim=0).contiguous()
-        kv = F.linear(ctx, self._w_kv)
+        ws = (self.to_k.weight, self.to_v.weight)
+        w = derived(self, "w_kv", ws, lambda: torch.cat(ws, dim=0).contiguous())
+        kv = dense_linear(ctx, w)
         c = self.inner_dim
         return kv[..., :c], kv[..., c:]
+
+    def out_proj(self, x):
+        """to_out[0] (+ the no-op dropout, pnp_utils.py:692-694).  When the transformer block has offered its
+        residual (`_residual`), the skip add of pnp_utils.py:283 / :315 rides in the GEMM epilogue."""
+        res, self._residual = self._residual, None
+        return dense_linear(x, self.to_out[0].weight, self.to_out[0].bias, res)
 
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, height=None, width=None,
                 **cross_attention_kwargs):
@@ -267,10 +308,9 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
     def forward(self, x):
-        if _STAGED and self.proj.in_features % 64 == 0 and self.proj.out_features % 128 == 0:
-            from . import staged
-
-            return staged.linear_geglu(x, self.proj.weight, self.proj.bias)
+        k, f2 = self.proj.in_features, self.proj.out_features
+        if _tc_ok(x, k, f2 // 2) and x.is_contiguous():
+            return ops.linear_geglu(x, self.proj.weight, self.proj.bias)   # gate in the GEMM epilogue
         return ops.geglu(self.proj(x))      # x * gelu(gate) in one pass (mvoc_geglu)
 
 
@@ -290,8 +330,9 @@ class FeedForward(nn.Module):
         self.net = nn.ModuleList([GEGLU(dim, inner) if activation_fn == "geglu" else GELU(dim, inner),
                                   nn.Dropout(0.0), nn.Linear(inner, dim)])
 
-    def forward(self, x):
-        return self.net[2](self.net[0](x))
+    def forward(self, x, residual=None):
+        out = self.net[2]
+        return dense_linear(self.net[0](x), out.weight, out.bias, residual)
 
 
 class BasicTransformerBlock(nn.Module):
@@ -315,12 +356,23 @@ class BasicTransformerBlock(nn.Module):
                 temporal: Optional[TemporalShape] = None):
         self.attn1.temporal = temporal
         self.attn2.temporal = temporal
-        h = self.attn1(self.norm1(hidden_states), encoder_hidden_states=None, height=height, width=width)
-        hidden_states = h.add_(hidden_states)                                   # :283
-        h = self.attn2(self.norm2(hidden_states), encoder_hidden_states=encoder_hidden_states)
-        hidden_states = h.add_(hidden_states)                                   # :315
-        h = self.ff(self.norm3(hidden_states))                                  # :322-335
-        return h.add_(hidden_states)                                            # :342
+        hidden_states = self._attend(self.attn1, self.norm1(hidden_states), hidden_states,
+                                     encoder_hidden_states=None, height=height, width=width)       # :283
+        hidden_states = self._attend(self.attn2, self.norm2(hidden_states), hidden_states,
+                                     encoder_hidden_states=encoder_hidden_states)                   # :315
+        return self.ff(self.norm3(hidden_states), residual=hidden_states)       # :322-342
+
+    @staticmethod
+    def _attend(attn, normed, residual, **kw):
+        """attn(normed) + residual.  The residual is offered to the processor's output projection
+        (Attention.out_proj fuses it into the GEMM epilogue); a processor that projects on its own leaves it
+        unconsumed and the add runs here."""
+        attn._residual = residual
+        h = attn(normed, **kw)
+        if attn._residual is None:
+            return h
+        attn._residual = None
+        return h.add_(residual)
 
 
 class Transformer2DModel(nn.Module):
@@ -342,12 +394,12 @@ class Transformer2DModel(nn.Module):
         n, height, width, C = hidden_states.shape
         inner = self.proj_in.out_channels
         x = self.norm(hidden_states)                                            # :430
-        tokens = F.linear(x.view(n, height * width, C), self.proj_in.weight.view(inner, C), self.proj_in.bias)
+        tokens = dense_linear(x.view(n, height * width, C), self.proj_in.weight.view(inner, C), self.proj_in.bias)
         for block in self.transformer_blocks:                                   # :487-497
             tokens = block(tokens, encoder_hidden_states=encoder_hidden_states, height=height, width=width)
-        out = F.linear(tokens, self.proj_out.weight.view(C, inner), self.proj_out.bias)   # :503
-        out = out.view(n, height, width, C).add_(hidden_states)                 # :508
-        return (out,)
+        out = dense_linear(tokens, self.proj_out.weight.view(C, inner), self.proj_out.bias,
+                           hidden_states.view(n, height * width, C))            # :503 + the skip add of :508
+        return (out.view(n, height, width, C),)
 
 
 class TransformerTemporalModel(nn.Module):
@@ -375,12 +427,12 @@ class TransformerTemporalModel(nn.Module):
         bt, height, width, C = hidden_states.shape
         b, S = bt // num_frames, height * width
         x = self.norm(hidden_states, frames_per_stat=num_frames, gather=gather)  # 5-D GroupNorm, :185-188
-        x = self.proj_in(x.view(bt, S, C))                                      # :191 (the permute at :189 is implicit)
+        x = dense_linear(x.view(bt, S, C), self.proj_in.weight, self.proj_in.bias)   # :191 (permute :189 implicit)
         shape = TemporalShape(b, num_frames, S)
         for block in self.transformer_blocks:                                   # :194-203
             x = block(x, encoder_hidden_states=None, height=height, width=width, temporal=shape)
-        x = self.proj_out(x)                                                    # :206
-        return x.view(bt, height, width, C).add_(hidden_states)                 # :207-215
+        x = dense_linear(x, self.proj_out.weight, self.proj_out.bias, hidden_states.view(bt, S, C))   # :206-215
+        return x.view(bt, height, width, C)
 
 
 # ------------------------------------------------------------------ conv blocks
@@ -401,7 +453,6 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
         self.feature_hook = None  # set by register_resnet_injection
         self.ctx: Optional[_Ctx] = None
-        self._bias2 = None
 
     def forward(self, input_tensor, temb, scale: float = 1.0):
         n, H, W, cin = input_tensor.shape
@@ -415,16 +466,17 @@ class ResnetBlock2D(nn.Module):
             h = conv_nhwc(h, self.conv2)                                        # :968
             self.feature_hook(self, h)                                          # :970-1004
             return h.add_(input_tensor)                                         # :1018
-        # 1x1 shortcut conv (:1011-1016) == row GEMM accumulated into conv2's output; its bias rides on
+        # 1x1 shortcut conv (:1011-1016) == extra K chunks of conv2's implicit GEMM; its bias rides on
         # conv2's (a per-channel constant commutes with the per-pixel select of the injection)
-        if self._bias2 is None or self._bias2.device != h.device or self._bias2.dtype != h.dtype:
-            self._bias2 = (self.conv2.bias + self.conv_shortcut.bias).detach()
-        h = conv_nhwc(h, self.conv2, bias=self._bias2)
-        if self.feature_hook is not None:
-            self.feature_hook(self, h)
+        sc = self.conv_shortcut
+        bias2 = derived(self, "bias2", (self.conv2.bias, sc.bias), lambda: (self.conv2.bias + sc.bias).detach())
+        if self.feature_hook is None:
+            return conv_nhwc(h, self.conv2, bias=bias2, shortcut=(input_tensor, sc))
+        h = conv_nhwc(h, self.conv2, bias=bias2)
+        self.feature_hook(self, h)                                              # blend BEFORE the shortcut add
         cout = h.shape[-1]
-        h.view(-1, cout).addmm_(input_tensor.view(-1, cin), self.conv_shortcut.weight.view(cout, cin).t())
-        return h
+        return dense_linear(input_tensor.view(-1, cin), sc.weight.view(cout, cin), None,
+                            h.view(-1, cout)).view(n, H, W, cout)
 
 
 class _TemporalTap(nn.Sequential):
@@ -439,7 +491,6 @@ class _TemporalTap(nn.Sequential):
             mods.append(nn.Dropout(0.0))
         mods.append(nn.Conv3d(dim_in, dim_out, (3, 1, 1), padding=(1, 0, 0)))
         super().__init__(*mods)
-        self._taps = None
 
     @property
     def norm(self):
@@ -449,17 +500,19 @@ class _TemporalTap(nn.Sequential):
     def conv(self):
         return self[len(self) - 1]
 
-    def forward(self, x, num_frames, gather=None):
-        """x: [(b t), h, w, C] frame-major channels-last -> same layout."""
+    def forward(self, x, num_frames, gather=None, residual=None):
+        """x: [(b t), h, w, C] frame-major channels-last -> same layout (+ residual, the layer's identity)."""
         bt, h, w, C = x.shape
         b, S = bt // num_frames, h * w
         y = self.norm(x, silu=True, frames_per_stat=num_frames, gather=gather)
         conv = self.conv
         co = conv.out_channels
-        if self._taps is None or self._taps.device != x.device or self._taps.dtype != x.dtype:
-            # [co, ci, 3, 1, 1] -> [tap, ci, co] (right-hand operands of the row GEMMs)
-            self._taps = conv.weight.view(co, C, 3).permute(2, 1, 0).contiguous()
-        wp, wc, wn = self._taps[0], self._taps[1], self._taps[2]
+        if _tc_ok(y, C, co):
+            wt = derived(self, "w_taps", (conv.weight,), lambda: ops.conv_taps(conv.weight))
+            return ops.temporal_conv3(y, wt, conv.bias, b, num_frames, residual)
+        # [co, ci, 3, 1, 1] -> [tap, ci, co] (right-hand operands of accumulating row GEMMs on frame-shifted rows)
+        taps = derived(self, "taps_t", (conv.weight,), lambda: conv.weight.view(co, C, 3).permute(2, 1, 0).contiguous())
+        wp, wc, wn = taps[0], taps[1], taps[2]
         y2 = y.view(bt * S, C)
         out = torch.addmm(conv.bias, y2, wc)                                    # centre tap, all frames
         rows = num_frames * S
@@ -468,7 +521,8 @@ class _TemporalTap(nn.Sequential):
                 r0, r1 = i * rows, (i + 1) * rows
                 out[r0 + S:r1].addmm_(y2[r0:r1 - S], wp)                        # tap on frame t-1
                 out[r0:r1 - S].addmm_(y2[r0 + S:r1], wn)                        # tap on frame t+1
-        return out.view(bt, h, w, co)
+        out = out.view(bt, h, w, co)
+        return out if residual is None else out.add_(residual)
 
 
 class TemporalConvLayer(nn.Module):
@@ -500,8 +554,7 @@ class TemporalConvLayer(nn.Module):
         h = self.conv1(hidden_states, num_frames, gather)                       # :1048
         h = self.conv2(h, num_frames, gather)
         h = self.conv3(h, num_frames, gather)
-        h = self.conv4(h, num_frames, gather)                                   # :1051
-        return h.add_(hidden_states)                                            # :1053
+        return self.conv4(h, num_frames, gather, residual=hidden_states)        # :1051 + identity :1053
 
 
 class Downsample2D(nn.Module):
@@ -524,8 +577,7 @@ class Upsample2D(nn.Module):
             xc = F.interpolate(xc, scale_factor=2.0, mode="nearest")
         else:
             xc = F.interpolate(xc, size=output_size, mode="nearest")
-        y = F.conv2d(xc, self.conv.weight, self.conv.bias, 1, 1).permute(0, 2, 3, 1)
-        return y if y.is_contiguous() else y.contiguous()
+        return conv_nhwc(xc.permute(0, 2, 3, 1), self.conv)
 
 
 class _Block3D(nn.Module):
@@ -761,6 +813,9 @@ class I2VGenXLUNet(nn.Module):
         for m in self.modules():
             if isinstance(m, (TransformerTemporalModel, TemporalConvLayer, Attention, ResnetBlock2D)):
                 m.ctx = self.ctx
+        # weights edited after the first forward: drop the cached re-layouts (and, through derived_epoch, the
+        # CUDA graphs that captured their addresses)
+        self.register_load_state_dict_post_hook(lambda module, incompatible: invalidate_derived(module))
 
     @property
     def dtype(self):

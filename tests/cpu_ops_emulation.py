@@ -164,23 +164,112 @@ def ddim_inverse_step_(pred_uncond, pred_cond, x, guidance, alpha_src, alpha_dst
     _ddim(pred_uncond, pred_cond, x, guidance, alpha_src, alpha_dst)
 
 
-def install(monkeypatch_or_module=None):
-    """Replace the kernel wrappers of mvoc_b200.ops with the emulations (tests only)."""
-    from mvoc_b200 import ops
+# ---- dense work (csrc/gemm_tc.cu): contracts of mvoc_linear / mvoc_linear_geglu / mvoc_conv3x3_nhwc /
+# mvoc_temporal_conv3.  `calls` counts what the host routed here (tests assert on it).
+calls = {"linear": 0, "linear_res": 0, "geglu": 0, "conv": 0, "conv_res": 0, "conv_shortcut": 0, "tconv": 0,
+         "tconv_res": 0}
+
+
+def _aligned(*dims):
+    assert all(d % 64 == 0 for d in dims), dims
+
+
+def linear(x, weight, bias=None, residual=None, out=None, variant=None):
+    n, k = weight.shape
+    _aligned(n, k)
+    assert weight.is_contiguous() and x.shape[-1] == k and x.stride(-1) == 1
+    assert out is None or (out.data_ptr() != x.data_ptr() and (residual is None or out.data_ptr() != residual.data_ptr()))
+    y = F.linear(x, weight, bias)
+    calls["linear"] += 1
+    if residual is not None:
+        assert residual.shape == y.shape and residual.stride(-1) == 1
+        calls["linear_res"] += 1
+        y = y + residual
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def linear_geglu(x, weight, bias=None, out=None, variant=None):
+    f2, k = weight.shape
+    _aligned(f2 // 2, k)
+    assert x.is_contiguous() and weight.is_contiguous()
+    calls["geglu"] += 1
+    v, g = F.linear(x, weight, bias).chunk(2, dim=-1)
+    return v * F.gelu(g)
+
+
+def conv3x3(x, w_taps, bias=None, residual=None, x2=None, w2=None, out=None, variant=None):
+    co, ci = w_taps.shape[1], w_taps.shape[2]
+    _aligned(co, ci)
+    assert x.dim() == 4 and x.is_contiguous() and w_taps.is_contiguous() and w_taps.shape[0] == 9
+    w = w_taps.view(3, 3, co, ci).permute(2, 3, 0, 1)
+    y = F.conv2d(x.permute(0, 3, 1, 2), w, bias, padding=1).permute(0, 2, 3, 1).contiguous()
+    calls["conv"] += 1
+    if x2 is not None:
+        c2 = x2.shape[-1]
+        _aligned(c2)
+        assert x2.is_contiguous() and tuple(x2.shape[:3]) == tuple(x.shape[:3]) and tuple(w2.shape) == (co, c2)
+        calls["conv_shortcut"] += 1
+        y = y + F.linear(x2, w2)
+    if residual is not None:
+        assert residual.shape == y.shape and residual.is_contiguous()
+        calls["conv_res"] += 1
+        y = y + residual
+    return y
+
+
+def temporal_conv3(x, w_taps, bias, videos, frames, residual=None, out=None, variant=None):
+    co, ci = w_taps.shape[1], w_taps.shape[2]
+    _aligned(co, ci)
+    assert x.is_contiguous() and x.shape[0] == videos * frames and w_taps.shape[0] == 3 and w_taps.is_contiguous()
+    xs = x.reshape(videos, frames, -1, ci)                                     # [b, t, s, ci]
+    y = torch.zeros(videos, frames, xs.shape[2], co, dtype=x.dtype)
+    for tap in range(3):
+        sh = tap - 1                                                           # frame offset of this tap
+        lo, hi = max(0, -sh), min(frames, frames - sh)
+        if hi > lo:
+            y[:, lo:hi] += F.linear(xs[:, lo + sh:hi + sh], w_taps[tap])
+    if bias is not None:
+        y = y + bias
+    y = y.reshape(x.shape[:-1] + (co,))
+    calls["tconv"] += 1
+    if residual is not None:
+        assert residual.shape == y.shape and residual.is_contiguous()
+        calls["tconv_res"] += 1
+        y = y + residual
+    return y
+
+
+def install(monkeypatch_or_module=None, dense: bool = True):
+    """Replace the kernel wrappers of mvoc_b200.ops with the emulations (tests only).  With `dense` the host's
+    routing predicate for the tcgen05 GEMM family is opened for CPU tensors too, so the weight re-layouts and
+    epilogue fusions of the product path (tap-major filters, fused QKV, residual / shortcut / GEGLU in the
+    epilogue) are what runs; without it the cuDNN / cuBLAS branch (MVOC_DENSE=lib) runs."""
+    from mvoc_b200 import ops, unet3d
 
     names = ["attention", "temporal_attention_frames", "temporal_attention", "qk_blend_", "feature_blend_",
-             "layernorm", "geglu", "latent_composite_", "cfg_ddim_step_", "ddim_inverse_step_"]
+             "layernorm", "geglu", "latent_composite_", "cfg_ddim_step_", "ddim_inverse_step_",
+             "linear", "linear_geglu", "conv3x3", "temporal_conv3"]
     saved = {n: getattr(ops, n) for n in names}
     for n in names:
         setattr(ops, n, globals()[n])
     # ops.groupnorm_nhwc itself (the slab-slicing wrapper) stays real; the kernel-calling piece is emulated
     saved["_groupnorm_nhwc_slab"] = ops._groupnorm_nhwc_slab
     ops._groupnorm_nhwc_slab = groupnorm_nhwc
+    saved["_tc_ok"] = unet3d._tc_ok
+    unet3d._tc_ok = (lambda x, k, n: k % 64 == 0 and n % 64 == 0) if dense else (lambda x, k, n: False)
+    for key in calls:
+        calls[key] = 0
     return saved
 
 
 def uninstall(saved):
-    from mvoc_b200 import ops
+    from mvoc_b200 import ops, unet3d
 
     for n, f in saved.items():
-        setattr(ops, n, f)
+        if n == "_tc_ok":
+            unet3d._tc_ok = f
+        else:
+            setattr(ops, n, f)

@@ -477,3 +477,65 @@ def test_bench_reference_arm_contract(monkeypatch, capsys):
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 4
     assert line["e2e"] == {"value": pytest.approx(0.002), "unit": "frames/s", "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
+
+
+# ------------------------------------------------------------------ round-2 advisor findings
+def test_mask_cache_never_aliases_recycled_addresses():
+    """Two compositions with different masks of the SAME shape in one process: the token masks must follow the
+    mask objects, not their addresses (the allocator hands a freed mask's address to the next one)."""
+    from mvoc_b200 import pnp_utils
+
+    cache = pnp_utils._MaskCache()
+    for it in range(6):
+        val = float(it % 2)
+        mf = torch.full((1, 4, 2, 8, 8), val)
+        mb = mf > 0.5
+        tok = cache.tokens([(mf, mb)], 4, 4, soft=False)
+        assert int(tok.sum()) == int(val) * tok.numel(), f"iteration {it}: stale token mask"
+        soft = cache.tokens([(mf, mb)], 4, 4, soft=True)
+        assert float(soft.sum()) == val * soft.numel()
+        feat = cache.feature_planes([(mf, mb)])
+        assert int(feat.sum()) == int(val) * feat.numel()
+        del mf, mb, tok, soft, feat
+    assert len(cache) <= cache.MAX_ENTRIES
+    # the same objects hit the same entry; an in-place edit of a mask invalidates it
+    mf = torch.zeros(1, 4, 2, 8, 8)
+    mb = mf > 0.5
+    h0 = cache.handle([(mf, mb)])
+    assert cache.handle([(mf, mb)]) is h0
+    mf.add_(1.0)
+    assert cache.handle([(mf, mb)]) is not h0
+
+
+def test_ops_refuse_tensors_of_another_device(monkeypatch):
+    """The C-ABI launches on the current device: a tensor living elsewhere must raise, not launch."""
+    from mvoc_b200 import ops
+
+    class _T:
+        is_cuda = True
+        device = torch.device("cuda", 1)
+
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    with pytest.raises(RuntimeError, match="current CUDA device"):
+        ops._need_cuda(_T())
+
+
+def test_scripts_fail_hard_on_missing_inputs(tmp_path):
+    """composite.py / inverse.py: missing latents, masks, conditioning or weights are errors unless --synthetic."""
+    from mvoc_b200 import composite, inverse
+
+    cfg = SimpleNamespace(video_name="vid", get=lambda k, d=None: d)
+    assert composite.conditioning_path("c/{video_name}.pt", cfg) == "c/vid.pt"
+    assert composite.build_parser().parse_args([]).synthetic is False
+    assert inverse.build_parser().parse_args(["--synthetic"]).synthetic is True
+    assert inverse.inversion_complete(str(tmp_path / "nope"), 4) is False
+    from mvoc_b200.pipeline import save_ddim_latents_at_t
+    from mvoc_b200.scheduler import DDIMSchedule
+
+    ts = DDIMSchedule(4, inverse=True).timesteps
+    for t in ts[:-1]:
+        save_ddim_latents_at_t(torch.zeros(1, 4, 2, 4, 4), t, str(tmp_path))
+    assert inverse.inversion_complete(str(tmp_path), 4) is False          # a partial run is not "done"
+    save_ddim_latents_at_t(torch.zeros(1, 4, 2, 4, 4), ts[-1], str(tmp_path))
+    assert inverse.inversion_complete(str(tmp_path), 4) is True
+    assert torch.load(os.path.join(str(tmp_path), f"ddim_latents_{int(ts[0])}.pt")).dtype == torch.float16

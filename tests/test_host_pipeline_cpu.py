@@ -210,42 +210,55 @@ def test_host_composite_frame_parallel(world):
     _run_fp(world)
 
 
-def test_host_staged_routing_vs_oracle(emulated_ops, monkeypatch):
-    """MVOC_STAGED=1 routing (stride-1 3x3 convolutions with tap-major weights and the fused residual, GEGLU
-    projection) with the staged kernels emulated in torch: same composition result as the oracle."""
-    import torch.nn.functional as F
-
-    from mvoc_b200 import staged, unet3d
+def test_host_dense_routing_vs_oracle(emulated_ops):
+    """The tcgen05 GEMM family is the product path: tap-major 3x3 / temporal filters, fused QKV, bias + residual,
+    the 1x1 shortcut conv inside conv2 and the GEGLU gate all ride in one call each.  With the kernels emulated in
+    torch the composition result equals the oracle, and every fusion is exercised."""
     from oracle import pipeline as opipe
+    from tests import cpu_ops_emulation as emu
 
-    calls = {"conv": 0, "conv_res": 0, "geglu": 0}
-
-    def conv3x3_nhwc(x, w_taps, bias=None, residual=None, out=None, variant=0):
-        co, ci = w_taps.shape[1], w_taps.shape[2]
-        assert x.is_contiguous() and w_taps.is_contiguous() and ci % 64 == 0 and co % 64 == 0
-        w = w_taps.view(3, 3, co, ci).permute(2, 3, 0, 1)
-        y = F.conv2d(x.permute(0, 3, 1, 2), w, bias, padding=1).permute(0, 2, 3, 1).contiguous()
-        calls["conv"] += 1
-        if residual is not None:
-            assert residual.shape == y.shape and residual.is_contiguous()
-            calls["conv_res"] += 1
-            y += residual
-        return y
-
-    def linear_geglu(x, weight, bias=None, out=None):
-        assert x.is_contiguous()
-        calls["geglu"] += 1
-        v, g = F.linear(x, weight, bias).chunk(2, dim=-1)
-        return v * F.gelu(g)
-
-    monkeypatch.setattr(unet3d, "_STAGED", True)
-    monkeypatch.setattr(staged, "conv3x3_nhwc", conv3x3_nhwc)
-    monkeypatch.setattr(staged, "linear_geglu", linear_geglu)
     wl, sched, inputs, ou = _setup("reduced2")
     ref = opipe.composite_loop(copy.deepcopy(ou), wl, inputs, max_steps=1)
     out = _composite(wl, sched, inputs, _product_cpu(ou, wl.unet), 1)
     assert rel_l2(out, ref) <= TOL
-    assert calls["conv"] > 0 and calls["conv_res"] > 0 and calls["geglu"] > 0
+    for key in ("linear", "linear_res", "geglu", "conv", "conv_res", "conv_shortcut", "tconv", "tconv_res"):
+        assert emu.calls[key] > 0, key
+
+
+def test_host_library_dense_path_vs_oracle():
+    """MVOC_DENSE=lib (the cuDNN / cuBLAS A/B baseline of bench.py) gives the same composition result."""
+    from oracle import pipeline as opipe
+    from tests import cpu_ops_emulation as emu
+
+    saved = emu.install(dense=False)
+    try:
+        wl, sched, inputs, ou = _setup("reduced2")
+        ref = opipe.composite_loop(copy.deepcopy(ou), wl, inputs, max_steps=1)
+        out = _composite(wl, sched, inputs, _product_cpu(ou, wl.unet), 1)
+        assert rel_l2(out, ref) <= TOL
+        assert emu.calls["linear"] == 0 and emu.calls["conv"] == 0
+    finally:
+        emu.uninstall(saved)
+
+
+def test_derived_weights_follow_load_state_dict(emulated_ops):
+    """Cached weight re-layouts (tap-major filters, fused QKV) are rebuilt after load_state_dict (advisor r1)."""
+    from mvoc_b200.unet3d import I2VGenXLUNet, UNetConfig, derived
+
+    m = I2VGenXLUNet(UNetConfig.named("reduced")).eval().requires_grad_(False)
+    attn = m.down_blocks[0].attentions[0].transformer_blocks[0].attn1
+    x = torch.randn(2, 4, attn.to_q.in_features)
+    q0 = attn.qkv_self(x)[0].clone()
+    epoch0 = m.__dict__.get("derived_epoch", 0)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    for k in sd:
+        if k.endswith("attn1.to_q.weight"):
+            sd[k] = sd[k] * 2.0
+    m.load_state_dict(sd)
+    assert m.__dict__["derived_epoch"] == epoch0 + 1
+    assert torch.allclose(attn.qkv_self(x)[0], 2.0 * q0, atol=1e-5)
+    attn.to_q.weight.mul_(0.5)                    # an in-place edit without load_state_dict is seen as well
+    assert torch.allclose(attn.qkv_self(x)[0], q0, atol=1e-5)
 
 
 def test_host_groupnorm_slabs_vs_oracle(emulated_ops, monkeypatch):

@@ -170,60 +170,75 @@ def section_time():
     print(f"  feature_blend l0: {t:.4f} ms  {by / t / 1e6:.0f} GB/s (min bytes)")
 
 
-def section_staged():
-    """Timings of the kernels staged in libmvoc_b200_staged.so against what the product path uses today."""
+def section_dense():
+    """The tcgen05 GEMM family (csrc/gemm_tc.cu) against the libraries it replaces, on the UNet's shapes."""
     import torch
     import torch.nn.functional as F
 
-    from mvoc_b200 import ops, staged
+    from mvoc_b200 import ops
 
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
-    print("== row-split attention vs product kernel (ms, TFLOP/s) ==")
-    for (B, H, N, Nk) in [(80, 5, 4096, 4096), (80, 10, 1024, 1024), (80, 20, 256, 256), (80, 5, 4096, 145)]:
-        C = H * 64
-        q = torch.randn(B, N, C, device=dev).bfloat16()
-        k = torch.randn(B, Nk, C, device=dev).bfloat16()
-        v = torch.randn(B, Nk, C, device=dev).bfloat16()
-        fl = 4.0 * B * H * N * Nk * 64
-        t = _time_cuda(lambda: ops.attention(q, k, v, H), iters=5)
-        print(f"  product      B={B} H={H} N={N} Nk={Nk}: {t:.3f} ms  {fl / t / 1e9:.1f} TF/s")
-        for variant in (0, 1, 2):
-            t = _time_cuda(lambda: staged.attention_split(q, k, v, H, variant=variant), iters=5)
-            print(f"  split v{variant}     B={B} H={H} N={N} Nk={Nk}: {t:.3f} ms  {fl / t / 1e9:.1f} TF/s")
+    torch.backends.cudnn.benchmark = True
+    variants = [int(v) for v in os.environ.get("MVOC_DIAG_VARIANTS", "0,1").split(",")]
     print("== 3x3 conv, channels-last (ms, TFLOP/s): tcgen05 implicit GEMM vs cuDNN ==")
     for (N, H, W, ci, co) in [(80, 64, 64, 320, 320), (80, 64, 64, 640, 320), (80, 64, 64, 960, 320),
-                              (80, 32, 32, 640, 640), (80, 32, 32, 1280, 640), (80, 16, 16, 1280, 1280),
-                              (80, 16, 16, 2560, 1280), (80, 8, 8, 1280, 1280)]:
+                              (80, 32, 32, 640, 640), (80, 32, 32, 1280, 640), (80, 32, 32, 1920, 640),
+                              (80, 16, 16, 1280, 1280), (80, 16, 16, 2560, 1280), (80, 8, 8, 1280, 1280),
+                              (80, 8, 8, 2560, 1280)]:
         x = torch.randn(N, H, W, ci, device=dev).bfloat16()
         w = (torch.randn(co, ci, 3, 3, device=dev) * (9 * ci) ** -0.5).bfloat16()
         b = torch.randn(co, device=dev).bfloat16()
-        wt = staged.prepare_conv_weight(w)
+        wt = ops.conv_taps(w)
         wcl = w.contiguous(memory_format=torch.channels_last)
         fl = 2.0 * N * H * W * co * ci * 9
         t = _time_cuda(lambda: F.conv2d(x.permute(0, 3, 1, 2), wcl, b, padding=1), iters=5)
         print(f"  cuDNN        {N}x{H}x{W} {ci}->{co}: {t:.3f} ms  {fl / t / 1e9:.1f} TF/s")
-        for variant in (0, 1, 2):
-            if variant == 2 and co % 320:
-                continue
-            t = _time_cuda(lambda: staged.conv3x3_nhwc(x, wt, b, None, variant=variant), iters=5)
-            print(f"  tcgen05 v{variant}   {N}x{H}x{W} {ci}->{co}: {t:.3f} ms  {fl / t / 1e9:.1f} TF/s")
-    print("== GEGLU projection (ms): fused epilogue vs cuBLAS + mvoc_geglu ==")
+        for v in variants:
+            t = _time_cuda(lambda: ops.conv3x3(x, wt, b, variant=v), iters=5)
+            print(f"  tcgen05 v{v}   {N}x{H}x{W} {ci}->{co}: {t:.3f} ms  {fl / t / 1e9:.1f} TF/s")
+    print("== Linear (ms, TFLOP/s): mvoc_linear (bias [+ residual] in the epilogue) vs cuBLAS (+ add_) ==")
+    for (M, K, N, res) in [(327680, 320, 960, 0), (327680, 320, 320, 1), (327680, 1280, 320, 1), (81920, 640, 1920, 0),
+                           (81920, 640, 640, 1), (81920, 2560, 640, 1), (20480, 1280, 3840, 0), (20480, 1280, 1280, 1),
+                           (20480, 5120, 1280, 1), (11600, 1024, 640, 0), (5120, 1280, 1280, 1)]:
+        x = torch.randn(M, K, device=dev).bfloat16()
+        w = (torch.randn(N, K, device=dev) * K ** -0.5).bfloat16()
+        b = torch.randn(N, device=dev).bfloat16()
+        r = torch.randn(M, N, device=dev).bfloat16() if res else None
+        fl = 2.0 * M * K * N
+        t = _time_cuda(lambda: F.linear(x, w, b).add_(r) if res else F.linear(x, w, b), iters=5)
+        print(f"  cuBLAS       M={M} K={K} N={N}{' +res' if res else ''}: {t:.3f} ms  {fl / t / 1e9:.1f} TF/s")
+        for v in variants:
+            t = _time_cuda(lambda: ops.linear(x, w, b, r, variant=v), iters=5)
+            print(f"  tcgen05 v{v}   M={M} K={K} N={N}{' +res' if res else ''}: {t:.3f} ms  {fl / t / 1e9:.1f} TF/s")
+    print("== GEGLU projection (ms): gate in the GEMM epilogue vs cuBLAS + mvoc_geglu ==")
     for (M, K) in [(327680, 320), (81920, 640), (20480, 1280)]:
         Fo = 4 * K
         x = torch.randn(M, K, device=dev).bfloat16()
         w = (torch.randn(2 * Fo, K, device=dev) * K ** -0.5).bfloat16()
         b = torch.randn(2 * Fo, device=dev).bfloat16()
-        t0 = _time_cuda(lambda: ops.geglu(F.linear(x, w, b)), iters=5)
-        t1 = _time_cuda(lambda: staged.linear_geglu(x, w, b), iters=5)
         fl = 2.0 * M * K * 2 * Fo
-        print(f"  M={M} K={K} F={Fo}: cuBLAS+geglu {t0:.3f} ms, fused {t1:.3f} ms ({fl / t1 / 1e9:.1f} TF/s)")
+        t0 = _time_cuda(lambda: ops.geglu(F.linear(x, w, b)), iters=5)
+        print(f"  cuBLAS+geglu M={M} K={K} F={Fo}: {t0:.3f} ms  {fl / t0 / 1e9:.1f} TF/s")
+        for v in variants:
+            t1 = _time_cuda(lambda: ops.linear_geglu(x, w, b, variant=v), iters=5)
+            print(f"  tcgen05 v{v}   M={M} K={K} F={Fo}: {t1:.3f} ms  {fl / t1 / 1e9:.1f} TF/s")
+    print("== temporal conv (3,1,1) (ms): one kernel vs 3 cuBLAS addmm per video ==")
+    for (B, T, S, C) in [(5, 16, 4096, 320), (5, 16, 1024, 640), (5, 16, 256, 1280), (5, 16, 64, 1280)]:
+        x = torch.randn(B * T, S, C, device=dev).bfloat16()
+        w = (torch.randn(C, C, 3, 1, 1, device=dev) * (3 * C) ** -0.5).bfloat16()
+        b = torch.randn(C, device=dev).bfloat16()
+        wt = ops.conv_taps(w)
+        fl = 2.0 * B * T * S * C * C * 3
+        for v in variants:
+            t = _time_cuda(lambda: ops.temporal_conv3(x, wt, b, B, T, variant=v), iters=5)
+            print(f"  tcgen05 v{v}   B={B} T={T} S={S} C={C}: {t:.3f} ms  {fl / t / 1e9:.1f} TF/s")
 
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
-    if what == "staged":
-        section_staged()
+    if what == "dense":
+        section_dense()
     if what in ("attn", "all"):
         section_attn()
     if what in ("time", "all"):
