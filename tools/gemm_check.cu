@@ -219,7 +219,7 @@ static int section_linear(int variant) {
 
 static int section_conv(int variant) {
     // N, H, W, Cin, Cout, Cin2 (1x1 shortcut source, 0 = none)
-    const int cases[][6] = {{2, 64, 64, 64, 64, 0},    {4, 32, 32, 128, 128, 0},  {16, 8, 8, 128, 160, 0},
+    const int cases[][6] = {{2, 64, 64, 64, 64, 0},    {4, 32, 32, 128, 128, 0},  {16, 8, 8, 128, 192, 0},
                             {3, 16, 16, 64, 320, 0},   {2, 11, 20, 64, 64, 0},    {5, 64, 64, 320, 320, 0},
                             {5, 8, 8, 64, 320, 128},   {5, 16, 16, 128, 640, 64}, {3, 22, 40, 64, 128, 0},
                             {5, 32, 32, 640, 640, 0},  {1, 64, 64, 960, 320, 960}};
