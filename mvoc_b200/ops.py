@@ -544,7 +544,7 @@ def temporal_attention_frames(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor,
 # --------------------------------------------------------------------------
 # bit 0 = CTA pairs (tcgen05 cta_group::2); bits 8.. = tile-width override.  An experiment switch for A/B
 # measurements (bench.py records it); the default is the configuration the product numbers were measured with.
-GEMM_VARIANT = int(os.environ.get("MVOC_GEMM_VARIANT", "0") or 0)
+GEMM_VARIANT = int(os.environ.get("MVOC_GEMM_VARIANT", "1") or 0)
 
 
 def _rows(t: torch.Tensor, what: str):
