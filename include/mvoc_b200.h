@@ -65,12 +65,12 @@ int mvoc_device_check(int device);
  *
  * q,o: [B, Nq, H, D]   k,v: [B, Nk, H, D]   D innermost and contiguous, D == 64.
  * Strides are in ELEMENTS for (batch, token, head).  Tensor-core path
- * (tcgen05.mma, accumulators in TMEM, operands staged by TMA); bf16 only.
- * Requirements: base pointers 16-byte aligned, strides multiples of 8.
- * variant: 0 = default (currently 4).  1 = P through shared memory (SS MMA), all exp2 on the MUFU;
- *          2 = P in TMEM (TS MMA), all exp2 on the MUFU; 3 / 4 / 5 = P in TMEM with 2 / 3 / 4 of every
+ * (tcgen05.mma, accumulators in TMEM, operands staged by TMA); bf16 or fp16 (P is rounded to the storage type).
+ * Requirements: base pointers 16-byte aligned, strides non-negative multiples of 8 (a batch stride of 0
+ * broadcasts one Q / K / V to every batch).
+ * variant: 0 = default (currently 4).  1, 2 = all exp2 on the MUFU; 3 / 4 / 5 = 2 / 3 / 4 of every
  *          8 exp2 pairs evaluated by a degree-3 polynomial on the FMA pipe.  Same results up to the exp2
- *          approximation (<= 1e-4 relative, below the bf16 rounding of P); the tests run all of them.
+ *          approximation (<= 1e-4 relative, below the 16-bit rounding of P); the tests run all of them.
  */
 int mvoc_attn_fwd(const void* q, const void* k, const void* v, void* o,
                   int B, int H, int Nq, int Nk, int D,
@@ -79,6 +79,22 @@ int mvoc_attn_fwd(const void* q, const void* k, const void* v, void* o,
                   int64_t v_sb, int64_t v_sn, int64_t v_sh,
                   int64_t o_sb, int64_t o_sn, int64_t o_sh,
                   float scale, int dtype, int variant, void* stream);
+
+/*
+ * Attention of a PAIR of branches that share Q and K: O[b] = softmax(Q[b] K[b]^T scale) V[b] and
+ * O[b + pair_batches] = (the same softmax) V[b + pair_batches], b < B.  One softmax, two P.V products per CTA —
+ * half the exponentials, which are what bounds a head_dim-64 attention on this chip.
+ * This is the structure MVOC creates and the reference ignores: ModifiedSpaAttnProcessor writes the SAME blended
+ * Q', K' into the uncond and the cond composite chunk (i2vgen-xl/pnp_utils.py:664-668) and then runs SDPA on
+ * both (:684).  q, k: [B, N, H, D]; v, o: [B + pair_batches, N, H, D]; other arguments as mvoc_attn_fwd.
+ */
+int mvoc_attn_pair_fwd(const void* q, const void* k, const void* v, void* o,
+                       int B, int H, int Nq, int Nk, int D,
+                       int64_t q_sb, int64_t q_sn, int64_t q_sh,
+                       int64_t k_sb, int64_t k_sn, int64_t k_sh,
+                       int64_t v_sb, int64_t v_sn, int64_t v_sh,
+                       int64_t o_sb, int64_t o_sn, int64_t o_sh,
+                       int pair_batches, float scale, int dtype, int variant, void* stream);
 
 /*
  * Short-sequence attention (tokens = frames), one warp per (pixel, head).
@@ -124,24 +140,32 @@ int mvoc_attn_temporal_strided_fwd(const void* q, const void* k, const void* v, 
 int mvoc_qk_blend(void* x0, void* x1, int n_obj, int64_t tokens, int C,
                   const void* mask, int mask_kind, int base_slot,
                   int dtype, void* stream);
+/* Same with a row stride `ld` (elements, >= C): x0 / x1 may be column slices of a wider row-major buffer, e.g. the
+ * Q and K thirds of a fused QKV projection.  single != 0 writes the blend to slot n_obj+1 only. */
+int mvoc_qk_blend_strided(void* x0, void* x1, int n_obj, int64_t tokens, int C, int64_t ld,
+                          const void* mask, int mask_kind, int base_slot, int single,
+                          int dtype, void* stream);
 
 /*
- * Injected self-attention in one call: mvoc_qk_blend followed by the attention of ALL branches on `stream`.
+ * Injected self-attention in one call: the Q/K mask blend followed by the attention of ALL branches on `stream`.
  * Replaces what ModifiedSpaAttnProcessor.__call__ does between the q/k/v projections and to_out
  * (i2vgen-xl/pnp_utils.py:624-686; mode MVOC_INJECT_SPATIAL, binary mask) and what
  * ModifiedTmpAttnProcessor.__call__ does there (:778-864; mode MVOC_INJECT_TEMPORAL, float mask).
  *
- * q, k, v, o: contiguous [(n_obj+3)*frames, pixels, H*D] — rows in (branch, frame, pixel) order in BOTH
- * modes (the temporal mode reads the frames of a pixel through strides; the [(b h w), T, C] permute of
- * :189 is not needed).  q and k are modified in place exactly like mvoc_qk_blend (slots n_obj+1, n_obj+2).
+ * q, k, v, o: [(n_obj+3)*frames, pixels, H*D] with row strides ld_q / ld_k / ld_v / ld_o (elements; rows of a
+ * branch-major, frame-major, pixel-minor token list) — q, k, v may be the three column slices of ONE fused QKV
+ * projection output, so the injected layers keep the single projection GEMM.  Rows are in (branch, frame, pixel)
+ * order in BOTH modes (the temporal mode reads the frames of a pixel through strides; the [(b h w), T, C] permute
+ * of :189 is not needed).  q and k are modified in place (slot n_obj+1, and slot n_obj+2 unless share_p).
  * mask: [n_obj, frames*pixels] in (frame, pixel) order, kind as for mvoc_qk_blend.
- * Restrictions of the attention kernels apply (D == 64, bf16; temporal: frames <= 32).
- * share_p: reserved for computing one softmax for the uncond/cond pair (they share Q', K' after the
- * injection, :664-668); must be 0, anything else returns MVOC_ERR_UNSUPPORTED.
- * Today this is two launches; it is the seam behind which the blend moves into the attention kernel.
+ * share_p (spatial mode): the uncond and cond composite branches receive the same blended Q', K' (:664-668), so
+ * their attention runs as ONE softmax with two P.V products (mvoc_attn_pair_fwd) and the blend writes one copy.
+ * Restrictions of the attention kernels apply (D == 64, bf16 / fp16; temporal: frames <= 32, share_p == 0).
  */
-int mvoc_attn_inject_fwd(void* q, void* k, const void* v, void* o, int n_obj, int frames, int64_t pixels,
-                         int H, int D, const void* mask, int mask_kind, int base_slot, int mode,
+int mvoc_attn_inject_fwd(void* q, void* k, const void* v, void* o,
+                         int64_t ld_q, int64_t ld_k, int64_t ld_v, int64_t ld_o,
+                         int n_obj, int frames, int64_t pixels, int H, int D,
+                         const void* mask, int mask_kind, int base_slot, int mode,
                          int share_p, float scale, int dtype, int variant, void* stream);
 
 /*

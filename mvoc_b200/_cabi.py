@@ -58,10 +58,18 @@ SIGNATURES = {
         c_int,
         [c_void_p, c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_void_p],
     ),
+    "mvoc_attn_pair_fwd": (
+        c_int,
+        [c_void_p] * 4 + [c_int] * 5 + [c_int64] * 12 + [c_int, c_float, c_int, c_int, c_void_p],
+    ),
+    "mvoc_qk_blend_strided": (
+        c_int,
+        [c_void_p, c_void_p, c_int, c_int64, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    ),
     "mvoc_attn_inject_fwd": (
         c_int,
-        [c_void_p] * 4 + [c_int, c_int, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_float,
-                          c_int, c_int, c_void_p],
+        [c_void_p] * 4 + [c_int64] * 4 + [c_int, c_int, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                          c_float, c_int, c_int, c_void_p],
     ),
     "mvoc_feature_blend": (
         c_int,

@@ -3,6 +3,12 @@
 // and inside diffusers' AttnProcessor2_0 (reached through attention_forward,
 // i2vgen-xl/pnp_utils.py:348-385) — non-causal, no mask, no dropout, D = 64.
 //
+// Pair mode (kNV = 2): MVOC writes the SAME blended Q', K' to the uncond and cond composite slots
+// (i2vgen-xl/pnp_utils.py:664-668), so their score matrices are identical: one CTA computes S and the softmax once
+// and multiplies P with BOTH value tiles (two O accumulators) — half the exponentials for those two branches.  It
+// runs on 64-key blocks so that S + P + 2 O still fit the 256 TMEM columns that let two CTAs share an SM.
+// bf16 or fp16 storage (P is rounded to the storage type).
+//
 // One CTA = one 128-row query tile of one (batch, head); two CTAs per SM.
 //   warps 0-3  softmax: thread i owns query row i (= TMEM lane i), so row
 //              max / row sum need no shuffles; the score row lives in 128 registers
@@ -14,6 +20,7 @@
 // Q, K, V are read straight from the projection output [B, N, H*64] through
 // 4-D tensor maps (128-byte swizzle), so no head transpose is ever materialised.
 #include <cuda.h>
+#include <type_traits>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -21,21 +28,21 @@ namespace mvoc {
 namespace attn {
 
 constexpr int BM = 128;  // query rows per CTA
-constexpr int BN = 128;  // keys per iteration
 constexpr int HD = 64;   // head dim
-constexpr int TILE_BYTES = BM * HD * 2;  // 16 KB: 128 rows x 128 B
+constexpr int Q_BYTES = BM * HD * 2;  // 16 KB: 128 rows x 128 B
 constexpr int THREADS = 256;  // warps 0-3 softmax (warpgroup 0); 4 TMA, 5 MMA, 6-7 idle (warpgroup 1)
 constexpr uint32_t TMEM_COLS = 256;
-constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192;
 constexpr float RESCALE_LOG2_THRESHOLD = 8.0f;
 
-template <bool kPInTmem, int kStages>
+// kBN keys per iteration, kNV value tensors sharing one softmax.  TMEM columns (fp32): S [0, kBN), P [kBN, 1.5 kBN)
+// (16-bit pairs), O_v [1.5 kBN + 64 v, +64).
+template <int kBN, int kNV, int kStages>
 struct Smem {
+    static constexpr int KV_BYTES = kBN * HD * 2;
     static constexpr int q_off = 0;
-    static constexpr int k_off = TILE_BYTES;
-    static constexpr int v_off = k_off + kStages * TILE_BYTES;
-    static constexpr int p_off = v_off + kStages * TILE_BYTES;
-    static constexpr int bar_off = p_off + (kPInTmem ? 0 : 2 * TILE_BYTES);
+    static constexpr int k_off = Q_BYTES;
+    static constexpr int v_off = k_off + kStages * KV_BYTES;
+    static constexpr int bar_off = v_off + kStages * kNV * KV_BYTES;
     // barriers: q_full, s_full, s_free, p_full, pv_done, k_full[], k_empty[], v_full[], v_empty[]
     static constexpr int n_bars = 5 + 4 * kStages;
     static constexpr int tmem_ptr_off = bar_off + n_bars * 8;
@@ -43,22 +50,49 @@ struct Smem {
     // No alignment slack: the dynamic window is declared __align__(1024) and checked at run time.  Two CTAs
     // must fit one SM: 2 * (alloc + 1 KB reserved) <= 228 KB — with the 3-stage ring that leaves < 2 KB.
     static constexpr int alloc = total;
+    static constexpr uint32_t COL_S = 0, COL_P = kBN, COL_O = kBN + kBN / 2;
     static_assert(2 * (alloc + 1024) <= 233472, "two CTAs per SM no longer fit in shared memory");
+    static_assert(COL_O + 64 * kNV <= TMEM_COLS, "S + P + O accumulators exceed the CTA's TMEM columns");
+    static_assert(kBN == 64 || kBN == 128, "key block of 64 or 128");
 };
 
 struct Params {
-    __nv_bfloat16* o;
+    void* o;
     int64_t o_sb, o_sn, o_sh;
     int Nq, Nk;
+    int pair_batches;   // kNV == 2: the second value / output tensor is this many batches after the first
     float scale_log2;
 };
 
+template <typename T> struct Pack2;
+template <> struct Pack2<__nv_bfloat16> {
+    static __device__ __forceinline__ uint32_t rn(float lo, float hi) {
+        __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&b);
+    }
+};
+template <> struct Pack2<__half> {
+    static __device__ __forceinline__ uint32_t rn(float lo, float hi) {
+        __half2 b = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<uint32_t*>(&b);
+    }
+};
+// kind::f16 instruction descriptor for 16-bit storage type T (fp16: format 0, bf16: format 1), fp32 accumulation
+template <typename T> __host__ __device__ constexpr uint32_t idesc_for(int M, int N, int b_mn_major) {
+    return (1u << 4) | ((std::is_same<T, __half>::value ? 0u : 1u) << 7) |
+           ((std::is_same<T, __half>::value ? 0u : 1u) << 10) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // kEmuMask: bit (k % 8) set => the k-th pair of a score row takes the FMA-pipe exp2 instead of the MUFU.
-template <bool kPInTmem, int kStages, uint32_t kEmuMask>
+template <typename T, int kBN, int kNV, int kStages, uint32_t kEmuMask>
 __global__ void __launch_bounds__(THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const Params prm) {
-    using L = Smem<kPInTmem, kStages>;
+    using L = Smem<kBN, kNV, kStages>;
+    constexpr int BN = kBN;
+    constexpr int KV_BYTES = L::KV_BYTES;
+    constexpr uint32_t COL_S = L::COL_S, COL_P = L::COL_P, COL_O = L::COL_O;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t sbase = smem_u32(smem_raw);
     uint8_t* sgen = smem_raw;
@@ -70,7 +104,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t sQ = sbase + L::q_off;
     const uint32_t sK = sbase + L::k_off;
     const uint32_t sV = sbase + L::v_off;
-    const uint32_t sP = sbase + L::p_off;
     const uint32_t bars = sbase + L::bar_off;
     const uint32_t b_q_full = bars, b_s_full = bars + 8, b_s_free = bars + 16, b_p_full = bars + 24,
                    b_pv_done = bars + 32;
@@ -116,7 +149,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (warp == 4) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            ptx::mbar_expect_tx(b_q_full, TILE_BYTES);
+            ptx::mbar_expect_tx(b_q_full, Q_BYTES);
             ptx::tma_load_4d(sQ, &tm_q, b_q_full, 0, h, m_blk * BM, b);
         }
         for (int j = 0; j < n_blocks; ++j) {
@@ -124,25 +157,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const uint32_t ph = (uint32_t)(j / kStages) & 1u;
             ptx::mbar_wait(b_k_empty + 8 * s, ph ^ 1u, 1);
             if (lane == 0) {
-                ptx::mbar_expect_tx(b_k_full + 8 * s, TILE_BYTES);
-                ptx::tma_load_4d(sK + s * TILE_BYTES, &tm_k, b_k_full + 8 * s, 0, h, j * BN, b);
+                ptx::mbar_expect_tx(b_k_full + 8 * s, KV_BYTES);
+                ptx::tma_load_4d(sK + s * KV_BYTES, &tm_k, b_k_full + 8 * s, 0, h, j * BN, b);
             }
             ptx::mbar_wait(b_v_empty + 8 * s, ph ^ 1u, 2);
             if (lane == 0) {
-                ptx::mbar_expect_tx(b_v_full + 8 * s, TILE_BYTES);
-                ptx::tma_load_4d(sV + s * TILE_BYTES, &tm_v, b_v_full + 8 * s, 0, h, j * BN, b);
+                ptx::mbar_expect_tx(b_v_full + 8 * s, kNV * KV_BYTES);
+#pragma unroll
+                for (int v = 0; v < kNV; ++v)
+                    ptx::tma_load_4d(sV + (s * kNV + v) * KV_BYTES, &tm_v, b_v_full + 8 * s, 0, h, j * BN,
+                                     b + v * prm.pair_batches);
             }
             __syncwarp();
         }
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t IDESC_QK = ptx::idesc_bf16(BM, BN, 0, 0);  // A,B K-major
-        constexpr uint32_t IDESC_PV = ptx::idesc_bf16(BM, HD, 0, 1);  // B (=V) MN-major
+        constexpr uint32_t IDESC_QK = idesc_for<T>(BM, BN, 0);  // A,B K-major
+        constexpr uint32_t IDESC_PV = idesc_for<T>(BM, HD, 1);  // B (=V) MN-major
         const uint32_t tS = tmem + COL_S, tP = tmem + COL_P, tO = tmem + COL_O;
         auto issue_qk = [&](int j) {
             const int s = j % kStages;
             const uint64_t a0 = ptx::smem_desc_sw128(sQ, 16, 1024);
-            const uint64_t b0 = ptx::smem_desc_sw128(sK + s * TILE_BYTES, 16, 1024);
+            const uint64_t b0 = ptx::smem_desc_sw128(sK + s * KV_BYTES, 16, 1024);
 #pragma unroll
             for (int ks = 0; ks < HD / 16; ++ks)  // +32 B per 16-element K step (encoded >>4)
                 ptx::mma_ss(tS, a0 + (uint64_t)(ks * 2), b0 + (uint64_t)(ks * 2), IDESC_QK, ks > 0);
@@ -170,18 +206,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             ptx::tc_fence_after();
             if (lane == 0) {
                 // V tile: rows = keys (K of this GEMM), 128 B per row = 64 d (N) contiguous
-                const uint64_t bv = ptx::smem_desc_sw128(sV + s * TILE_BYTES, 16384, 1024);
 #pragma unroll
-                for (int ks = 0; ks < BN / 16; ++ks) {
-                    const uint64_t bd = bv + (uint64_t)((ks * 2048) >> 4);
-                    const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
-                    if (kPInTmem) {
-                        ptx::mma_ts(tO, tP + ks * 8, bd, IDESC_PV, acc);
-                    } else {
-                        const uint64_t ap = ptx::smem_desc_sw128(
-                            sP + (ks >> 2) * TILE_BYTES + (ks & 3) * 32, 16, 1024);
-                        ptx::mma_ss(tO, ap, bd, IDESC_PV, acc);
-                    }
+                for (int v = 0; v < kNV; ++v) {
+                    const uint64_t bv = ptx::smem_desc_sw128(sV + (s * kNV + v) * KV_BYTES, 16384, 1024);
+#pragma unroll
+                    for (int ks = 0; ks < BN / 16; ++ks)
+                        ptx::mma_ts(tO + v * HD, tP + ks * 8, bv + (uint64_t)((ks * 2048) >> 4), IDESC_PV,
+                                    (j > 0 || ks > 0) ? 1u : 0u);
                 }
                 ptx::tc_commit(b_v_empty + 8 * s);
                 ptx::tc_commit(b_pv_done);
@@ -241,7 +272,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     if (need) m_used = m_new;
                     l_sum *= f;
 #pragma unroll
-                    for (int c = 0; c < HD / 32; ++c) {
+                    for (int c = 0; c < kNV * HD / 32; ++c) {
                         uint32_t o[32];
                         ptx::tmem_ld32(tO + c * 32, o);
                         ptx::tmem_wait_ld();
@@ -276,8 +307,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 else if ((k & 3) == 1) lb = ptx::add2(lb, p2);
                 else if ((k & 3) == 2) lc = ptx::add2(lc, p2);
                 else ld = ptx::add2(ld, p2);
-                __nv_bfloat162 b = __floats2bfloat162_rn(p0, p1);
-                pk[k] = *reinterpret_cast<uint32_t*>(&b);
+                pk[k] = Pack2<T>::rn(p0, p1);
             }
             {
                 float s0, s1;
@@ -289,46 +319,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 ptx::mbar_wait(b_pv_done, (uint32_t)(j - 1) & 1u, 11);
                 ptx::tc_fence_after();
             }
-            if (kPInTmem) {
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
-                    ptx::tmem_st32(tP + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[c * 32]));
-                ptx::tmem_wait_st();
-                ptx::tc_fence_before();
-            } else {
-                // row `row` of two K-major 128B-swizzled tiles (keys 0-63, 64-127)
-#pragma unroll
-                for (int cc = 0; cc < 16; ++cc) {
-                    const uint32_t addr = sP + (cc >> 3) * TILE_BYTES + row * 128 +
-                                          (((cc & 7) ^ (row & 7)) << 4);
-                    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr),
-                                 "r"(pk[cc * 4]), "r"(pk[cc * 4 + 1]), "r"(pk[cc * 4 + 2]),
-                                 "r"(pk[cc * 4 + 3])
-                                 : "memory");
-                }
-                ptx::fence_proxy_async_smem();
-            }
+            for (int c = 0; c < BN / 64; ++c)
+                ptx::tmem_st32(tP + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[c * 32]));
+            ptx::tmem_wait_st();
+            ptx::tc_fence_before();
             ptx::mbar_arrive(b_p_full);
         }
-        // ---- epilogue: O / l -> bf16 -> global --------------------------------
+        // ---- epilogue: O / l -> 16-bit -> global --------------------------------
         ptx::mbar_wait(b_pv_done, (uint32_t)(n_blocks - 1) & 1u, 12);
         ptx::tc_fence_after();
         const float inv_l = 1.0f / l_sum;
         const int q_row = m_blk * BM + row;
-        __nv_bfloat16* orow = prm.o + (int64_t)b * prm.o_sb + (int64_t)q_row * prm.o_sn +
-                              (int64_t)h * prm.o_sh;
 #pragma unroll
-        for (int c = 0; c < HD / 32; ++c) {
-            uint32_t r[32];
-            ptx::tmem_ld32(tO + c * 32, r);
-            ptx::tmem_wait_ld();
-            if (q_row < prm.Nq) {
+        for (int v = 0; v < kNV; ++v) {
+            T* orow = reinterpret_cast<T*>(prm.o) + (int64_t)(b + v * prm.pair_batches) * prm.o_sb +
+                      (int64_t)q_row * prm.o_sn + (int64_t)h * prm.o_sh;
 #pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    float f[8];
+            for (int c = 0; c < HD / 32; ++c) {
+                uint32_t r[32];
+                ptx::tmem_ld32(tO + v * HD + c * 32, r);
+                ptx::tmem_wait_ld();
+                if (q_row < prm.Nq) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[i + e]) * inv_l;
-                    *reinterpret_cast<Vec16*>(orow + c * 32 + i) = pack8<__nv_bfloat16>(f);
+                    for (int i = 0; i < 32; i += 8) {
+                        float f[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[i + e]) * inv_l;
+                        *reinterpret_cast<Vec16*>(orow + c * 32 + i) = pack8<T>(f);
+                    }
                 }
             }
         }
@@ -359,21 +378,21 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// [B, N, H, 64] bf16 with element strides (sb, sn, sh); box = 128 tokens x 64 of one head.
-static int make_map(CUtensorMap* m, const void* base, int B, int H, int N, int64_t sb, int64_t sn,
+// [B, N, H, 64] 16-bit with element strides (sb, sn, sh); box = `rows` tokens x 64 of one head.
+static int make_map(CUtensorMap* m, const void* base, int dtype, int B, int H, int N, int rows, int64_t sb, int64_t sn,
                     int64_t sh, const char* what) {
     EncodeTiledFn fn = get_encode_fn();
     MVOC_REQUIRE(fn != nullptr, MVOC_ERR_DRIVER, "mvoc_attn_fwd: cuTensorMapEncodeTiled unavailable");
     cuuint64_t dims[4] = {(cuuint64_t)HD, (cuuint64_t)H, (cuuint64_t)N, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)sh * 2, (cuuint64_t)sn * 2, (cuuint64_t)sb * 2};
-    // a size-1 dimension may carry any stride; TMA still wants a multiple of 16 bytes
+    // a size-1 dimension may carry any stride; TMA still wants a non-zero multiple of 16 bytes
     if (H == 1) strides[0] = 128;
-    if (B == 1) strides[2] = (cuuint64_t)sn * 2 * (cuuint64_t)N;
-    cuuint32_t box[4] = {(cuuint32_t)HD, 1, (cuuint32_t)BM, 1};
+    if (B == 1 || strides[2] == 0) strides[2] = (cuuint64_t)sn * 2 * (cuuint64_t)N;
+    cuuint32_t box[4] = {(cuuint32_t)HD, 1, (cuuint32_t)rows, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
-                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = fn(m, dtype == MVOC_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     MVOC_REQUIRE(r == CUDA_SUCCESS, MVOC_ERR_DRIVER,
                  "mvoc_attn_fwd: cuTensorMapEncodeTiled(%s) failed with CUresult %d "
                  "(B=%d H=%d N=%d strides=%lld,%lld,%lld)",
@@ -381,21 +400,79 @@ static int make_map(CUtensorMap* m, const void* base, int B, int H, int N, int64
     return MVOC_OK;
 }
 
-template <bool kPInTmem, int kStages, uint32_t kEmuMask>
-static int launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
-                  const Params& prm, int B, int H, cudaStream_t s) {
-    using L = Smem<kPInTmem, kStages>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<kPInTmem, kStages, kEmuMask>,
+template <typename T, int kBN, int kNV, int kStages, uint32_t kEmuMask>
+static int launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const Params& prm, int B, int H,
+                  cudaStream_t s) {
+    using L = Smem<kBN, kNV, kStages>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<T, kBN, kNV, kStages, kEmuMask>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, L::alloc);
-        MVOC_REQUIRE(e == cudaSuccess, MVOC_ERR_CUDA, "mvoc_attn_fwd: cudaFuncSetAttribute: %s",
-                     cudaGetErrorString(e));
-        attr_set = true;
+        MVOC_REQUIRE(e == cudaSuccess, MVOC_ERR_CUDA, "mvoc_attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set[dev] = true;
     }
     dim3 grid((prm.Nq + BM - 1) / BM, H, B);
-    attn_fwd_kernel<kPInTmem, kStages, kEmuMask><<<grid, THREADS, L::alloc, s>>>(mq, mk, mv, prm);
+    attn_fwd_kernel<T, kBN, kNV, kStages, kEmuMask><<<grid, THREADS, L::alloc, s>>>(mq, mk, mv, prm);
     return check_launch("mvoc_attn_fwd");
+}
+
+// Common entry: kNV value tensors per softmax (1 = plain attention, 2 = the uncond/cond pair).
+static int run(const void* q, const void* k, const void* v, void* o, int B, int H, int Nq, int Nk, int D,
+               const int64_t (&st)[12], int pair_batches, float scale, int dtype, int variant, void* stream,
+               const char* what) {
+    MVOC_REQUIRE(q && k && v && o, MVOC_ERR_INVALID_ARG, "%s: null pointer", what);
+    MVOC_REQUIRE(dtype == MVOC_BF16 || dtype == MVOC_F16, MVOC_ERR_UNSUPPORTED, "%s: dtype %d unsupported (bf16 / fp16)",
+                 what, dtype);
+    MVOC_REQUIRE(D == HD, MVOC_ERR_UNSUPPORTED, "%s: head_dim %d unsupported (64 only)", what, D);
+    MVOC_REQUIRE(B > 0 && H > 0 && Nq > 0 && Nk > 0, MVOC_ERR_INVALID_ARG, "%s: empty problem B=%d H=%d Nq=%d Nk=%d", what,
+                 B, H, Nq, Nk);
+    MVOC_REQUIRE(B <= 65535 && H <= 65535, MVOC_ERR_UNSUPPORTED, "%s: B=%d / H=%d exceed the grid limits", what, B, H);
+    MVOC_REQUIRE(variant >= 0 && variant <= 5, MVOC_ERR_INVALID_ARG, "%s: unknown variant %d", what, variant);
+    MVOC_REQUIRE(pair_batches >= 0, MVOC_ERR_INVALID_ARG, "%s: pair_batches=%d", what, pair_batches);
+    for (int i = 0; i < 12; ++i)
+        MVOC_REQUIRE(st[i] % 8 == 0 && st[i] >= 0, MVOC_ERR_UNSUPPORTED,
+                     "%s: stride #%d = %lld is not a non-negative multiple of 8 elements", what, i, (long long)st[i]);
+    MVOC_REQUIRE(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) &&
+                     ((uintptr_t)o % 16 == 0),
+                 MVOC_ERR_INVALID_ARG, "%s: pointers must be 16-byte aligned", what);
+    const bool pair = pair_batches > 0;
+    const int kv_rows = pair ? 64 : 128;
+    CUtensorMap mq, mk, mv;
+    int rc;
+    if ((rc = make_map(&mq, q, dtype, B, H, Nq, BM, st[0], st[1], st[2], "q")) != MVOC_OK) return rc;
+    if ((rc = make_map(&mk, k, dtype, B, H, Nk, kv_rows, st[3], st[4], st[5], "k")) != MVOC_OK) return rc;
+    if ((rc = make_map(&mv, v, dtype, B + pair_batches, H, Nk, kv_rows, st[6], st[7], st[8], "v")) != MVOC_OK) return rc;
+    Params prm;
+    prm.o = o;
+    prm.o_sb = st[9];
+    prm.o_sn = st[10];
+    prm.o_sh = st[11];
+    prm.Nq = Nq;
+    prm.Nk = Nk;
+    prm.pair_batches = pair_batches;
+    prm.scale_log2 = scale * 1.4426950408889634f;
+    cudaStream_t s = (cudaStream_t)stream;
+    // variants (same results up to the exp2 approximation; the tests run all of them):
+    //   1, 2: all exponentials on the MUFU;  3 / 4 / 5: 2 / 3 / 4 of every 8 pairs on the FMA-pipe polynomial;  0: default
+    const uint32_t emu = variant == 1 || variant == 2 ? 0x00u : variant == 3 ? 0x88u : variant == 5 ? 0xAAu : 0xA8u;
+#define MVOC_ATTN_LAUNCH(T, BN, NV, EMU) launch<T, BN, NV, 3, EMU>(mq, mk, mv, prm, B, H, s)
+#define MVOC_ATTN_EMU(T, BN, NV)                                           \
+    switch (emu) {                                                         \
+        case 0x00u: return MVOC_ATTN_LAUNCH(T, BN, NV, 0x00u);             \
+        case 0x88u: return MVOC_ATTN_LAUNCH(T, BN, NV, 0x88u);             \
+        case 0xAAu: return MVOC_ATTN_LAUNCH(T, BN, NV, 0xAAu);             \
+        default: return MVOC_ATTN_LAUNCH(T, BN, NV, 0xA8u); /* fastest measured on B200 */ \
+    }
+    if (dtype == MVOC_F16) {
+        if (pair) { MVOC_ATTN_EMU(__half, 64, 2) }
+        MVOC_ATTN_EMU(__half, 128, 1)
+    }
+    if (pair) { MVOC_ATTN_EMU(__nv_bfloat16, 64, 2) }
+    MVOC_ATTN_EMU(__nv_bfloat16, 128, 1)
+#undef MVOC_ATTN_EMU
+#undef MVOC_ATTN_LAUNCH
 }
 
 }  // namespace attn
@@ -408,50 +485,17 @@ extern "C" int mvoc_attn_fwd(const void* q, const void* k, const void* v, void* 
                              int64_t k_sb, int64_t k_sn, int64_t k_sh, int64_t v_sb, int64_t v_sn,
                              int64_t v_sh, int64_t o_sb, int64_t o_sn, int64_t o_sh, float scale,
                              int dtype, int variant, void* stream) {
-    MVOC_REQUIRE(q && k && v && o, MVOC_ERR_INVALID_ARG, "mvoc_attn_fwd: null pointer");
-    MVOC_REQUIRE(dtype == MVOC_BF16, MVOC_ERR_UNSUPPORTED,
-                 "mvoc_attn_fwd: dtype %d unsupported (bf16 only)", dtype);
-    MVOC_REQUIRE(D == attn::HD, MVOC_ERR_UNSUPPORTED,
-                 "mvoc_attn_fwd: head_dim %d unsupported (64 only)", D);
-    MVOC_REQUIRE(B > 0 && H > 0 && Nq > 0 && Nk > 0, MVOC_ERR_INVALID_ARG,
-                 "mvoc_attn_fwd: empty problem B=%d H=%d Nq=%d Nk=%d", B, H, Nq, Nk);
-    MVOC_REQUIRE(B <= 65535 && H <= 65535, MVOC_ERR_UNSUPPORTED,
-                 "mvoc_attn_fwd: B=%d / H=%d exceed the grid limits", B, H);
-    MVOC_REQUIRE(variant >= 0 && variant <= 5, MVOC_ERR_INVALID_ARG,
-                 "mvoc_attn_fwd: unknown variant %d", variant);
-    const int64_t strides[12] = {q_sb, q_sn, q_sh, k_sb, k_sn, k_sh, v_sb, v_sn, v_sh, o_sb, o_sn, o_sh};
-    for (int i = 0; i < 12; ++i)
-        MVOC_REQUIRE(strides[i] % 8 == 0 && strides[i] >= 0, MVOC_ERR_UNSUPPORTED,
-                     "mvoc_attn_fwd: stride #%d = %lld is not a non-negative multiple of 8 elements",
-                     i, (long long)strides[i]);
-    MVOC_REQUIRE(((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) &&
-                     ((uintptr_t)o % 16 == 0),
-                 MVOC_ERR_INVALID_ARG, "mvoc_attn_fwd: pointers must be 16-byte aligned");
-    CUtensorMap mq, mk, mv;
-    int rc;
-    if ((rc = attn::make_map(&mq, q, B, H, Nq, q_sb, q_sn, q_sh, "q")) != MVOC_OK) return rc;
-    if ((rc = attn::make_map(&mk, k, B, H, Nk, k_sb, k_sn, k_sh, "k")) != MVOC_OK) return rc;
-    if ((rc = attn::make_map(&mv, v, B, H, Nk, v_sb, v_sn, v_sh, "v")) != MVOC_OK) return rc;
-    attn::Params prm;
-    prm.o = (__nv_bfloat16*)o;
-    prm.o_sb = o_sb;
-    prm.o_sn = o_sn;
-    prm.o_sh = o_sh;
-    prm.Nq = Nq;
-    prm.Nk = Nk;
-    prm.scale_log2 = scale * 1.4426950408889634f;
-    cudaStream_t s = (cudaStream_t)stream;
-    // variants (same results up to the exp2 approximation; the tests run all of them):
-    //   1: P through shared memory (SS MMA), all exponentials on the MUFU
-    //   2: P in TMEM (TS MMA), all exponentials on the MUFU
-    //   3 / 4 / 5: P in TMEM, 2 / 3 / 4 of every 8 pairs on the FMA-pipe polynomial
-    //   0: default
-    switch (variant) {
-        case 1: return attn::launch<false, 2, 0x00u>(mq, mk, mv, prm, B, H, s);
-        case 2: return attn::launch<true, 3, 0x00u>(mq, mk, mv, prm, B, H, s);
-        case 3: return attn::launch<true, 3, 0x88u>(mq, mk, mv, prm, B, H, s);
-        case 5: return attn::launch<true, 3, 0xAAu>(mq, mk, mv, prm, B, H, s);
-        case 4:
-        default: return attn::launch<true, 3, 0xA8u>(mq, mk, mv, prm, B, H, s);  // fastest measured on B200
-    }
+    const int64_t st[12] = {q_sb, q_sn, q_sh, k_sb, k_sn, k_sh, v_sb, v_sn, v_sh, o_sb, o_sn, o_sh};
+    return attn::run(q, k, v, o, B, H, Nq, Nk, D, st, 0, scale, dtype, variant, stream, "mvoc_attn_fwd");
+}
+
+extern "C" int mvoc_attn_pair_fwd(const void* q, const void* k, const void* v, void* o, int B, int H,
+                                  int Nq, int Nk, int D, int64_t q_sb, int64_t q_sn, int64_t q_sh,
+                                  int64_t k_sb, int64_t k_sn, int64_t k_sh, int64_t v_sb, int64_t v_sn,
+                                  int64_t v_sh, int64_t o_sb, int64_t o_sn, int64_t o_sh, int pair_batches,
+                                  float scale, int dtype, int variant, void* stream) {
+    const int64_t st[12] = {q_sb, q_sn, q_sh, k_sb, k_sn, k_sh, v_sb, v_sn, v_sh, o_sb, o_sn, o_sh};
+    MVOC_REQUIRE(pair_batches > 0, MVOC_ERR_INVALID_ARG, "mvoc_attn_pair_fwd: pair_batches=%d must be positive",
+                 pair_batches);
+    return attn::run(q, k, v, o, B, H, Nq, Nk, D, st, pair_batches, scale, dtype, variant, stream, "mvoc_attn_pair_fwd");
 }

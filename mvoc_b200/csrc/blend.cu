@@ -15,10 +15,12 @@ struct QKBlendParams {
     void* x[2];
     const void* mask;
     int64_t tokens;
-    int64_t chunk_elems;  // tokens * C
+    int64_t ld;           // row stride in elements (>= C): rows may be column slices of a wider buffer
+    int64_t chunk_elems;  // tokens * ld: distance between branch slots
     int C;
     int n_obj;
     int base_slot;
+    int single;           // write the blend to the uncond slot only (the pair kernel reads it for both composites)
 };
 
 // One item = one 16-byte piece of one token row.  blockIdx.y picks Q or K.
@@ -31,7 +33,7 @@ __global__ void __launch_bounds__(256) qk_blend_kernel(QKBlendParams p) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += stride) {
         const int64_t tok = it / vec_per_tok;
-        const int64_t off = it << 3;  // element offset inside a slot: tok*C + v*8
+        const int64_t off = tok * p.ld + ((it - tok * vec_per_tok) << 3);  // element offset inside a slot
         if (!kSoft) {
             const uint8_t* m = reinterpret_cast<const uint8_t*>(p.mask);
             int src = p.base_slot;
@@ -40,7 +42,7 @@ __global__ void __launch_bounds__(256) qk_blend_kernel(QKBlendParams p) {
                 if (__ldg(m + (int64_t)j * p.tokens + tok)) src = j + 1;
             const Vec16 v = ld_stream16(x + (int64_t)src * p.chunk_elems + off);
             st_stream16(x + (int64_t)u_slot * p.chunk_elems + off, v);
-            if (src != c_slot) st_stream16(x + (int64_t)c_slot * p.chunk_elems + off, v);
+            if (src != c_slot && !p.single) st_stream16(x + (int64_t)c_slot * p.chunk_elems + off, v);
         } else {
             const float* m = reinterpret_cast<const float*>(p.mask);
             float acc[8];
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(256) qk_blend_kernel(QKBlendParams p) {
             }
             const Vec16 v = pack8<T>(acc);
             st_stream16(x + (int64_t)u_slot * p.chunk_elems + off, v);
-            if (touched || p.base_slot != c_slot)
+            if ((touched || p.base_slot != c_slot) && !p.single)
                 st_stream16(x + (int64_t)c_slot * p.chunk_elems + off, v);
         }
     }
@@ -119,8 +121,16 @@ using namespace mvoc;
 extern "C" int mvoc_qk_blend(void* x0, void* x1, int n_obj, int64_t tokens, int C,
                              const void* mask, int mask_kind, int base_slot, int dtype,
                              void* stream) {
+    return mvoc_qk_blend_strided(x0, x1, n_obj, tokens, C, C, mask, mask_kind, base_slot, 0, dtype, stream);
+}
+
+extern "C" int mvoc_qk_blend_strided(void* x0, void* x1, int n_obj, int64_t tokens, int C, int64_t ld,
+                                     const void* mask, int mask_kind, int base_slot, int single, int dtype,
+                                     void* stream) {
     MVOC_REQUIRE(x0 != nullptr && mask != nullptr, MVOC_ERR_INVALID_ARG,
                  "mvoc_qk_blend: null pointer");
+    MVOC_REQUIRE(ld >= C && ld % 8 == 0, MVOC_ERR_INVALID_ARG,
+                 "mvoc_qk_blend: row stride %lld must be a multiple of 8 and >= C=%d", (long long)ld, C);
     MVOC_REQUIRE(n_obj >= 1 && n_obj <= MVOC_MAX_OBJECTS, MVOC_ERR_INVALID_ARG,
                  "mvoc_qk_blend: n_obj=%d out of range [1,%d]", n_obj, MVOC_MAX_OBJECTS);
     MVOC_REQUIRE(base_slot == 0 || base_slot == n_obj + 2, MVOC_ERR_INVALID_ARG,
@@ -139,10 +149,12 @@ extern "C" int mvoc_qk_blend(void* x0, void* x1, int n_obj, int64_t tokens, int 
     p.x[1] = x1;
     p.mask = mask;
     p.tokens = tokens;
-    p.chunk_elems = tokens * C;
+    p.ld = ld;
+    p.chunk_elems = tokens * ld;
     p.C = C;
     p.n_obj = n_obj;
     p.base_slot = base_slot;
+    p.single = single ? 1 : 0;
     const int64_t items = tokens * (C / 8);
     dim3 grid(grid_for(items, 256, 16), x1 ? 2 : 1);
     cudaStream_t s = (cudaStream_t)stream;

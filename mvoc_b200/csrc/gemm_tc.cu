@@ -36,9 +36,7 @@ namespace gemm {
 constexpr int BM = 128;                    // rows (pixels) per CTA tile
 constexpr int KC = 64;                     // K elements per stage = one 128-byte swizzled row
 constexpr int A_BYTES = BM * KC * 2;       // 16 KB
-constexpr int SLAB = 32;                   // output columns per epilogue slab (64-byte rows, 64B swizzle)
-constexpr int SLAB_BYTES = BM * SLAB * 2;  // 8 KB
-constexpr int N_OUT = 4;                   // staging buffers of the epilogue
+constexpr int N_OUT = 3;                   // staging buffers per epilogue warp (residual prefetched two slabs ahead)
 constexpr int THREADS = 192;
 constexpr int SMEM_LIMIT = 232448;         // 227 KB per CTA
 constexpr uint32_t TMEM_COLS = 512;
@@ -55,14 +53,18 @@ struct Cfg {
     static constexpr int B_BYTES = B_ROWS * KC * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int OUT_COLS = kEpi == EPI_GEGLU ? BN / 2 : BN;   // output columns of a tile
+    // epilogue slab: 64 columns (128-byte rows, 128B swizzle) when the tile divides into them, else 32 (64B swizzle);
+    // the GEGLU epilogue holds value AND gate columns in registers, so it stays at 32
+    static constexpr int SLAB = (kEpi == EPI_LINEAR && OUT_COLS % 64 == 0) ? 64 : 32;
     static constexpr int SLABS = OUT_COLS / SLAB;
+    static constexpr int WSLAB_BYTES = 32 * SLAB * 2;        // one warp's 32 rows of one slab: 2 or 4 KB
     static constexpr int out_off = 0;                        // staging first: 1024-byte aligned like the stages
-    static constexpr int stage_off = N_OUT * SLAB_BYTES;
+    static constexpr int stage_off = 4 * N_OUT * WSLAB_BYTES;
     static constexpr int kStagesFit = (SMEM_LIMIT - stage_off - 512) / STAGE_BYTES;
     static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr int bar_off = stage_off + kStages * STAGE_BYTES;
-    // barriers: full[kStages], empty[kStages], acc_full[2], acc_empty[2], res_full[N_OUT]
-    static constexpr int n_bars = 2 * kStages + 4 + N_OUT;
+    // barriers: full[kStages], empty[kStages], acc_full[2], acc_empty[2], res_full[4 warps][N_OUT]
+    static constexpr int n_bars = 2 * kStages + 4 + 4 * N_OUT;
     static constexpr int tmem_ptr_off = bar_off + n_bars * 8;
     static constexpr int alloc = tmem_ptr_off + 16;
     static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "BN: multiple of 32 in [64, 256]");
@@ -186,6 +188,20 @@ __device__ __forceinline__ Vec16 ldg16_nc(const void* p) {
     return v;
 }
 
+// x -> 0.5 x (1 + erf(x / sqrt 2)): exact GELU (torch.nn.functional.gelu default).  erf by Abramowitz-Stegun 7.1.26
+// (|error| <= 1.5e-7, far below the 16-bit rounding of the product): one reciprocal, one exp2, a degree-5 Horner.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float t = fabsf(x) * 0.70710678118654752f;
+    const float k = __frcp_rn(fmaf(0.3275911f, t, 1.0f));
+    float p = fmaf(1.061405429f, k, -1.453152027f);
+    p = fmaf(p, k, 1.421413741f);
+    p = fmaf(p, k, -0.284496736f);
+    p = fmaf(p, k, 0.254829592f);
+    const float e = ptx::ex2_approx(-1.4426950408889634f * t * t);
+    const float erf_abs = fmaf(-p * k, e, 1.0f);         // erf(|x| / sqrt 2)
+    return 0.5f * x + 0.5f * fabsf(x) * erf_abs;          // 0.5 x (1 + sign(x) erf(|x| / sqrt 2))
+}
+
 // Instruction descriptor kind::f16: 16-bit inputs (kF16 ? fp16 : bf16), fp32 accumulation, A and B K-major.
 __host__ __device__ constexpr uint32_t idesc_16(int M, int N, bool f16) {
     return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) |
@@ -255,7 +271,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
             ptx::mbar_init(b_acc_full + 8 * b, 1);
             ptx::mbar_init(b_acc_empty + 8 * b, C::kTwoCta ? 8 : 4);   // one arrive per epilogue warp (of both CTAs)
         }
-        for (int b = 0; b < N_OUT; ++b) ptx::mbar_init(b_res + 8 * b, 1);
+        for (int b = 0; b < 4 * N_OUT; ++b) ptx::mbar_init(b_res + 8 * b, 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_t<C::kTwoCta>(s_tmem_ptr, TMEM_COLS);
@@ -336,31 +352,41 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
             }
         }
     } else {
-        // ===================== epilogue (warps 2-5) =====================
-        const int q = warp & 3;                        // TMEM lane quarter this warp may read
-        const int row = q * 32 + lane;                 // row of the tile == TMEM lane
-        const bool issuer = threadIdx.x == 64;         // warp 2, lane 0: owns the bulk-async groups
-        const uint32_t row_off = (uint32_t)row * 64u;
-        const uint32_t sw = (uint32_t)((row >> 1) & 3);   // 64-byte swizzle: 16-byte chunk c lives at c ^ sw
+        // ===================== epilogue (warps 2-5), one independent pipeline per warp =====================
+        // Warp q owns rows [32q, 32q+32) of the tile (the TMEM lanes it may read).  Per slab of SLAB columns:
+        // tcgen05.ld (issued one slab ahead) -> + bias -> (+ residual, TMA-loaded into the staging buffer two slabs
+        // ahead) -> (GEGLU) -> 16-bit -> swizzled staging -> TMA store of the warp's own 32-row box.  No barrier
+        // wider than the warp: lane 0 owns the warp's bulk-async groups and residual barriers.
+        constexpr int SLAB = C::SLAB, SLABS = C::SLABS;
+        constexpr int CHUNKS = SLAB / 8;                    // 16-byte chunks per staged row
+        const int q = warp & 3;
+        const uint32_t sWarp = sOut + (uint32_t)q * (N_OUT * C::WSLAB_BYTES);
+        const uint32_t row_off = (uint32_t)lane * (SLAB * 2);
+        // swizzle of the staging rows (what the TMA store expects): 128B -> chunk ^ (row & 7); 64B -> chunk ^ ((row >> 1) & 3)
+        const uint32_t sw = SLAB == 64 ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+        const uint32_t b_res_w = b_res + 8 * (q * N_OUT);
         const T* bias = reinterpret_cast<const T*>(prm.bias);
+        // rows 32q.. of the tile inside the (b1, b2, b3) row box
+        const int r0 = q * 32;
+        const int w1 = r0 % prm.b1, w2 = (r0 / prm.b1) % prm.b2, w3 = r0 / (prm.b1 * prm.b2);
 
-        // slab g of this CTA -> (valid, output column, row coordinates)
-        auto slab_at = [&](uint32_t g, int& col, TileCoord& tc) -> bool {
-            const int t = first_tile + (int)(g / C::SLABS) * tile_stride;
+        auto slab_at = [&](uint32_t g, int& col, TileCoord& tc) -> bool {   // slab g of this CTA -> column, row coords
+            const int t = first_tile + (int)(g / SLABS) * tile_stride;
             if (t >= prm.total_tiles) return false;
             tc = decode_tile<C>(prm, t, crank);
-            col = tc.n_tile * C::OUT_COLS + (int)(g % C::SLABS) * SLAB;
+            col = tc.n_tile * C::OUT_COLS + (int)(g % SLABS) * SLAB;
             return true;
         };
-        auto prefetch_res = [&](uint32_t g) {
+        auto prefetch_res = [&](uint32_t g) {   // lane 0 only
             int col;
             TileCoord tc;
             if (!slab_at(g, col, tc)) return;
             const uint32_t ob = g % N_OUT;
-            ptx::mbar_expect_tx(b_res + 8 * ob, SLAB_BYTES);
-            ptx::tma_load_4d(sOut + ob * SLAB_BYTES, &tm_res, b_res + 8 * ob, col, tc.c1, tc.c2, tc.c3);
+            ptx::mbar_expect_tx(b_res_w + 8 * ob, C::WSLAB_BYTES);
+            ptx::tma_load_4d(sWarp + ob * C::WSLAB_BYTES, &tm_res, b_res_w + 8 * ob, col, tc.c1 + w1, tc.c2 + w2,
+                             tc.c3 + w3);
         };
-        if (issuer && prm.has_res) {
+        if (lane == 0 && prm.has_res) {
             prefetch_res(0);
             prefetch_res(1);
         }
@@ -372,36 +398,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
             ptx::tc_fence_after();
             const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + buf * C::BN;
             const int col0 = tc.n_tile * C::OUT_COLS;
-#pragma unroll 1
-            for (int sl = 0; sl < C::SLABS; ++sl, ++g) {
-                const uint32_t ob = g % N_OUT;
-                const uint32_t sbuf = sOut + ob * SLAB_BYTES + row_off;
-                uint32_t r[32];
-                ptx::tmem_ld32(tacc + sl * SLAB, r);
-                uint32_t gt[32];
-                if (C::kEpi == EPI_GEGLU) ptx::tmem_ld32(tacc + C::BN / 2 + sl * SLAB, gt);
-                ptx::tmem_wait_ld();
-                if (sl == C::SLABS - 1) {   // accumulator buffer drained: hand it back to the MMA warp
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (C::kTwoCta) mbar_arrive_leader(b_acc_empty + 8 * buf);
-                        else ptx::mbar_arrive(b_acc_empty + 8 * buf);
-                    }
-                }
-                if (prm.has_res) ptx::mbar_wait(b_res + 8 * ob, (g / N_OUT) & 1u, 5);
+            uint32_t r[2][SLAB];                               // value columns, two slabs in flight
+            uint32_t gt[C::kEpi == EPI_GEGLU ? SLAB : 1];      // gate columns (GEGLU)
+            auto issue_ld = [&](int sl, int which) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < SLAB / 32; ++c)
+                    ptx::tmem_ld32(tacc + sl * SLAB + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[which][c * 32]));
+                if constexpr (C::kEpi == EPI_GEGLU)
+                    ptx::tmem_ld32(tacc + C::BN / 2 + sl * SLAB, *reinterpret_cast<uint32_t(*)[32]>(&gt[0]));
+            };
+            auto release_acc = [&]() {                       // accumulator buffer drained: back to the MMA warp
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (C::kTwoCta) mbar_arrive_leader(b_acc_empty + 8 * buf);
+                    else ptx::mbar_arrive(b_acc_empty + 8 * buf);
+                }
+            };
+            auto process = [&](int sl, const uint32_t (&acc)[SLAB]) {
+                const uint32_t ob = g % N_OUT;
+                const uint32_t sbuf = sWarp + ob * C::WSLAB_BYTES + row_off;
+                if (prm.has_res) ptx::mbar_wait(b_res_w + 8 * ob, (g / N_OUT) & 1u, 5);
+#pragma unroll
+                for (int c = 0; c < CHUNKS; ++c) {
                     float f[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[c * 8 + e]);
+                    for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(acc[c * 8 + e]);
                     if (bias) {
                         float bv[8];
                         unpack8<T>(ldg16_nc(bias + col0 + sl * SLAB + c * 8), bv);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[e] += bv[e];
                     }
-                    if (C::kEpi == EPI_GEGLU) {
+                    if constexpr (C::kEpi == EPI_GEGLU) {
                         float gv[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) gv[e] = __uint_as_float(gt[c * 8 + e]);
@@ -412,8 +441,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                             for (int e = 0; e < 8; ++e) gv[e] += bg[e];
                         }
 #pragma unroll
-                        for (int e = 0; e < 8; ++e)   // exact (erf) GELU, as torch.nn.functional.gelu
-                            f[e] *= 0.5f * gv[e] * (1.0f + erff(gv[e] * 0.70710678118654752f));
+                        for (int e = 0; e < 8; ++e) f[e] *= gelu_erf(gv[e]);
                     }
                     const uint32_t addr = sbuf + (((uint32_t)c ^ sw) << 4);
                     if (prm.has_res) {
@@ -425,16 +453,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                     sts16(addr, pack8<T>(f));
                 }
                 ptx::fence_proxy_async_smem();          // generic-proxy writes -> visible to the TMA store
-                if (issuer) bulk_wait_read<1>();        // the store of slab g-2 has released its buffer
-                named_bar_sync(1, 128);
-                if (issuer) {
-                    tma_store_4d(&tm_out, sOut + ob * SLAB_BYTES, col0 + sl * SLAB, tc.c1, tc.c2, tc.c3);
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_4d(&tm_out, sWarp + ob * C::WSLAB_BYTES, col0 + sl * SLAB, tc.c1 + w1, tc.c2 + w2, tc.c3 + w3);
                     ptx::bulk_commit();
-                    if (prm.has_res) prefetch_res(g + 2);   // into the buffer slab g-2 used
+                    bulk_wait_read<1>();                 // stores up to slab g-1 have released their buffers
+                    if (prm.has_res) prefetch_res(g + 2);   // into the buffer slab g-1 used
+                }
+                ++g;
+            };
+            if constexpr (C::kEpi == EPI_GEGLU) {
+                // the gate makes this epilogue compute-heavy (one erf per output): keep the code small (no unrolling
+                // across slabs: the unrolled form overflowed the instruction cache and ran 1.7x slower on B200)
+#pragma unroll 1
+                for (int sl = 0; sl < SLABS; ++sl) {
+                    issue_ld(sl, 0);
+                    ptx::tmem_wait_ld();
+                    if (sl + 1 == SLABS) release_acc();
+                    process(sl, r[0]);
+                }
+            } else {
+                issue_ld(0, 0);
+#pragma unroll
+                for (int sl = 0; sl < SLABS; ++sl) {
+                    ptx::tmem_wait_ld();                     // slab sl is in r[sl & 1]
+                    if (sl + 1 < SLABS) issue_ld(sl + 1, (sl & 1) ^ 1);   // next slab streams in meanwhile
+                    else release_acc();
+                    process(sl, r[sl & 1]);
                 }
             }
         }
-        if (issuer) bulk_wait_all();
+        if (lane == 0) bulk_wait_all();
         ptx::tc_fence_before();
     }
 
@@ -487,11 +536,6 @@ static int make_map4(CUtensorMap* m, const void* base, int dtype, const int64_t 
     return MVOC_OK;
 }
 
-static int pow2_floor(int64_t v) {
-    int p = 1;
-    while ((int64_t)p * 2 <= v) p *= 2;
-    return p;
-}
 
 // Row box (b1, b2, b3), powers of two with product 128, that wastes the fewest zero-filled rows on the
 // (d1, d2, d3) grid; ties go to the widest box along d1 (longest contiguous runs).
@@ -561,14 +605,14 @@ static int launch_cfg(const Problem& pb, Params prm, int b1, int b2, int b3, cud
     }
     if (pb.n_src == 1) ma[1] = ma[0], mw[1] = mw[0];
     {
+        // the epilogue stores per warp: a box of 32 rows (the first 32 rows of the row box) x SLAB columns
+        const int sb1 = b1 < 32 ? b1 : 32, sb2 = b2 < 32 / sb1 ? b2 : 32 / sb1, sb3 = 32 / (sb1 * sb2);
         const int64_t dims[4] = {pb.N, pb.d1, pb.d2, pb.d3};
-        const int box[4] = {SLAB, b1, b2, b3};
-        if ((rc = make_map4(&mo, pb.out, pb.dtype, dims, pb.out_str, box, CU_TENSOR_MAP_SWIZZLE_64B, what)) != MVOC_OK)
-            return rc;
+        const int box[4] = {C::SLAB, sb1, sb2, sb3};
+        const CUtensorMapSwizzle swz = C::SLAB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+        if ((rc = make_map4(&mo, pb.out, pb.dtype, dims, pb.out_str, box, swz, what)) != MVOC_OK) return rc;
         if (pb.residual) {
-            if ((rc = make_map4(&mr, pb.residual, pb.dtype, dims, pb.res_str, box, CU_TENSOR_MAP_SWIZZLE_64B, what)) !=
-                MVOC_OK)
-                return rc;
+            if ((rc = make_map4(&mr, pb.residual, pb.dtype, dims, pb.res_str, box, swz, what)) != MVOC_OK) return rc;
         } else {
             mr = mo;
         }

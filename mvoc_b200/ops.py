@@ -217,18 +217,50 @@ def qk_blend_(
     _count()
 
 
+def attention_pair(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, pair_batches: int,
+                   scale: Optional[float] = None, out: Optional[torch.Tensor] = None, variant: int = 0) -> torch.Tensor:
+    """Two branches that share Q and K (mvoc_attn_pair_fwd): q, k [B, N, H*64]; v [B + pair_batches, N, H*64];
+    out[b] = softmax(q[b] k[b]^T) v[b], out[b + pair_batches] = the same softmax times v[b + pair_batches]."""
+    _need_cuda(q, k, v, out)
+    B, Nq, C = q.shape
+    Nk = k.shape[1]
+    if k.shape[0] != B or v.shape[0] != B + pair_batches or v.shape[1] != Nk or pair_batches < 1:
+        raise ValueError(f"attention_pair: q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)} pair {pair_batches}")
+    if out is None:
+        out = torch.empty((B + pair_batches, Nq, C), dtype=q.dtype, device=q.device)
+    if scale is None:
+        scale = HEAD_DIM ** -0.5
+    with _Timed(("attn_pair", B, heads, Nq, Nk), 2 * 4.0 * B * heads * Nq * Nk * HEAD_DIM):
+        st = _cabi.load().mvoc_attn_pair_fwd(
+            q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, heads, Nq, Nk, HEAD_DIM,
+            *_bnc_strides(q, heads), *_bnc_strides(k, heads), *_bnc_strides(v, heads), *_bnc_strides(out, heads),
+            int(pair_batches), float(scale), _dt(q), int(variant), _stream())
+    _cabi.check(st, "mvoc_attn_pair_fwd")
+    _count()
+    return out
+
+
+def _token_rows(t: torch.Tensor, what: str, batches: int, pixels: int, C: int) -> int:
+    """Row stride (elements) of a [batches, pixels, C] tensor whose (batch, pixel) rows are uniformly strided — a
+    contiguous tensor or a column slice of a wider row-major buffer (e.g. one third of a fused QKV output)."""
+    if tuple(t.shape) != (batches, pixels, C) or t.stride(2) != 1 or t.stride(0) != pixels * t.stride(1):
+        raise ValueError(f"attention_inject_: {what} must be [{batches}, {pixels}, {C}] with uniformly strided rows, "
+                         f"got {tuple(t.shape)} strides {t.stride()}")
+    return t.stride(1)
+
+
 def attention_inject_(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask: torch.Tensor, heads: int, n_obj: int,
                       frames: int, inject_background: bool, temporal: bool, scale: Optional[float] = None,
-                      out: Optional[torch.Tensor] = None, variant: int = 0) -> torch.Tensor:
+                      out: Optional[torch.Tensor] = None, variant: int = 0, share_p: Optional[bool] = None) -> torch.Tensor:
     """Q/K injection + attention of all branches through the single C-ABI call mvoc_attn_inject_fwd.
-    q, k, v: contiguous [(n_obj+3)*frames, pixels, H*64], rows in (branch, frame, pixel) order for the spatial
-    AND the temporal mode; mask [n_obj, frames*pixels] uint8 / float32.  q and k are modified in place."""
+    q, k, v: [(n_obj+3)*frames, pixels, H*64], rows in (branch, frame, pixel) order for the spatial AND the temporal
+    mode, uniformly strided (they may be the column slices of one fused QKV GEMM output); mask [n_obj,
+    frames*pixels] uint8 / float32.  q and k are modified in place.  share_p (default: on for the spatial mode): one
+    softmax for the uncond / cond pair, which receive the same blended Q', K'."""
     _need_cuda(q, k, v, mask, out)
     nb = n_obj + 3
-    if q.dim() != 3 or q.shape[0] != nb * frames or k.shape != q.shape or v.shape != q.shape:
+    if q.dim() != 3 or q.shape[0] != nb * frames:
         raise ValueError(f"attention_inject_: need q, k, v [{nb}*{frames}, pixels, C], got {tuple(q.shape)}")
-    if not (q.is_contiguous() and k.is_contiguous() and v.is_contiguous()):
-        raise ValueError("attention_inject_: q, k, v must be contiguous")
     pixels, C = q.shape[1], q.shape[2]
     if C != heads * HEAD_DIM:
         raise ValueError(f"attention_inject_: C={C} != heads*{HEAD_DIM}")
@@ -241,17 +273,26 @@ def attention_inject_(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mask: t
     if tuple(mask.shape) != (n_obj, frames * pixels) or not mask.is_contiguous():
         raise ValueError(f"attention_inject_: mask must be contiguous [{n_obj}, {frames * pixels}]")
     if out is None:
-        out = torch.empty_like(q)
-    elif out.shape != q.shape or not out.is_contiguous():
-        raise ValueError("attention_inject_: out must be contiguous and shaped like q")
+        out = torch.empty((nb * frames, pixels, C), dtype=q.dtype, device=q.device)
+    lds = [_token_rows(t, nm, nb * frames, pixels, C) for t, nm in ((q, "q"), (k, "k"), (v, "v"), (out, "out"))]
     if scale is None:
         scale = HEAD_DIM ** -0.5
+    if share_p is None:
+        share_p = not temporal
     base = 0 if inject_background else n_obj + 2
-    rc = _cabi.load().mvoc_attn_inject_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), n_obj, frames,
-                                           pixels, heads, HEAD_DIM, mask.data_ptr(), kind, base, int(bool(temporal)),
-                                           0, float(scale), _dt(q), int(variant), _stream())
+    rows = nb * frames * pixels
+    if temporal:
+        timed = _Timed(("attn_temporal", nb * pixels, heads, frames), 4.0 * rows * C * q.element_size())
+    else:   # algorithmic FLOPs of the reference: every branch runs its own softmax (pnp_utils.py:684)
+        timed = _Timed(("attn_inject", nb * frames, heads, pixels, pixels, int(bool(share_p))),
+                       4.0 * nb * frames * heads * pixels * pixels * HEAD_DIM)
+    with timed:
+        rc = _cabi.load().mvoc_attn_inject_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), *lds, n_obj,
+                                               frames, pixels, heads, HEAD_DIM, mask.data_ptr(), kind, base,
+                                               int(bool(temporal)), int(bool(share_p)), float(scale), _dt(q),
+                                               int(variant), _stream())
     _cabi.check(rc, "mvoc_attn_inject_fwd")
-    _count(2)
+    _count(3 if (share_p and not temporal) else 2)
     return out
 
 

@@ -26,7 +26,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .unet3d import AttnProcessor2_0, dense_linear, run_attention
+from .unet3d import AttnProcessor2_0
 
 MaskPair = Tuple[torch.Tensor, torch.Tensor]
 
@@ -166,12 +166,12 @@ class _InjectingProcessor(AttnProcessor2_0):
         nb = n_obj + 3
         if hidden_states.shape[0] % nb != 0:
             raise ValueError(f"batch {hidden_states.shape[0]} is not divisible into n_obj+3={nb} branches")
-        # separate projections: the blend kernel wants slot-major contiguous Q and K
-        q = dense_linear(hidden_states, attn.to_q.weight)                       # :604
-        k = dense_linear(hidden_states, attn.to_k.weight)                       # :611
-        v = dense_linear(hidden_states, attn.to_v.weight)                       # :612
+        # ONE fused QKV projection, as on the stock layers: the kernels take the three column slices with their
+        # row stride (the reference projects three times, :604-612)
+        q, k, v = attn.qkv_self(hidden_states)
         par = _partition(attn)
         n_frames_total = mask[0][0].shape[2]
+        frames = hidden_states.shape[0] // nb
         if self.temporal:
             if par is not None and attn.ctx.full_hw is not None:   # rows are this rank's pixel shard of (fh x fw)
                 fh, fw = attn.ctx.full_hw
@@ -181,8 +181,10 @@ class _InjectingProcessor(AttnProcessor2_0):
         else:
             frm = par.frame_range(n_frames_total) if par is not None else None
             tokens = _MASKS.tokens(mask, height, width, soft=False, frames=frm)  # binary mask (:648)
-        ops.qk_blend_(q, k, tokens, n_obj, bool(self.inject_background))         # :628-672 / :782-850
-        out = run_attention(q, k, v, attn.heads, attn.temporal)                  # :684 / :862
+        # blend (:628-672 / :782-850) + attention of every branch (:684 / :862) in one C-ABI call; on the spatial
+        # layers the uncond / cond pair shares one softmax (they receive the same Q', K': :664-668)
+        out = ops.attention_inject_(q, k, v, tokens, attn.heads, n_obj, frames, bool(self.inject_background),
+                                    self.temporal)
         return attn.out_proj(out)                                               # :692 (+ the block's skip add)
 
 

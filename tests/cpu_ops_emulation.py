@@ -72,6 +72,46 @@ def qk_blend_(q, k, mask, n_obj, inject_background):
         v[n_obj + 2] = acc
 
 
+def attention_pair(q, k, v, heads, pair_batches, scale=None, out=None, variant=0):
+    """out[b] = softmax(q[b] k[b]^T) v[b]; out[b + pair_batches] = the same softmax times v[b + pair_batches]."""
+    B = q.shape[0]
+    assert k.shape[0] == B and v.shape[0] == B + pair_batches and pair_batches >= 1
+    o = torch.empty((B + pair_batches,) + tuple(q.shape[1:]), dtype=q.dtype)
+    o[:B] = ops_ref.sdpa_ref(q.contiguous(), k.contiguous(), v[:B].contiguous(), heads)
+    o[pair_batches:] = ops_ref.sdpa_ref(q.contiguous(), k.contiguous(), v[pair_batches:].contiguous(), heads)
+    return o
+
+
+def attention_inject_(q, k, v, mask, heads, n_obj, frames, inject_background, temporal, scale=None, out=None,
+                      variant=0, share_p=None):
+    """Contract of mvoc_attn_inject_fwd: blend (one copy with share_p) + attention of every branch; q, k, v are
+    uniformly strided [(n_obj+3)*frames, pixels, C] views (column slices of a fused QKV buffer allowed)."""
+    nb = n_obj + 3
+    pixels, C = q.shape[1], q.shape[2]
+    if share_p is None:
+        share_p = not temporal
+    for t in (q, k, v):
+        assert tuple(t.shape) == (nb * frames, pixels, C) and t.stride(2) == 1 and t.stride(0) == pixels * t.stride(1)
+        assert t.stride(1) % 8 == 0
+    assert tuple(mask.shape) == (n_obj, frames * pixels) and mask.is_contiguous()
+    assert not (share_p and temporal)
+    base = 0 if inject_background else n_obj + 2
+    blended = []
+    for x in (q, k):
+        vw = x.reshape(nb, frames * pixels, C)
+        acc = vw[base].clone()
+        for j in range(n_obj):
+            m = mask[j].to(torch.float32)[:, None]
+            acc = torch.where(m != 0, vw[j + 1], acc) if mask.dtype == torch.uint8 else acc * (1 - m) + vw[j + 1] * m
+        blended.append(acc.view(frames, pixels, C))
+    qq = torch.cat([q[:(n_obj + 1) * frames], blended[0], blended[0]], dim=0)
+    kk = torch.cat([k[:(n_obj + 1) * frames], blended[1], blended[1]], dim=0)
+    if temporal:
+        return temporal_attention_frames(qq.reshape(-1, C), kk.reshape(-1, C), v.reshape(-1, C).contiguous(), heads, nb,
+                                         frames, pixels).view(nb * frames, pixels, C)
+    return ops_ref.sdpa_ref(qq, kk, v.contiguous(), heads)
+
+
 def feature_blend_(x, mask, n_obj, frames):
     nb = n_obj + 3
     assert x.dim() == 4 and x.is_contiguous() and x.shape[0] == nb * frames
@@ -249,7 +289,8 @@ def install(monkeypatch_or_module=None, dense: bool = True):
     epilogue) are what runs; without it the cuDNN / cuBLAS branch (MVOC_DENSE=lib) runs."""
     from mvoc_b200 import ops, unet3d
 
-    names = ["attention", "temporal_attention_frames", "temporal_attention", "qk_blend_", "feature_blend_",
+    names = ["attention", "attention_pair", "attention_inject_", "temporal_attention_frames", "temporal_attention",
+             "qk_blend_", "feature_blend_",
              "layernorm", "geglu", "latent_composite_", "cfg_ddim_step_", "ddim_inverse_step_",
              "linear", "linear_geglu", "conv3x3", "temporal_conv3"]
     saved = {n: getattr(ops, n) for n in names}

@@ -40,15 +40,35 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc == -1 and b"n_obj" in lib.mvoc_last_error()
     rc = lib.mvoc_cfg_ddim_step(16, 16, 16, 7, 1.0, 0.5, 0.6, 0, 2, None)
     assert rc == -2 and b"multiple of 8" in lib.mvoc_last_error()
-    inj = lambda **kw: lib.mvoc_attn_inject_fwd(*[{**dict(q=16, k=16, v=16, o=16, n_obj=2, frames=2, pixels=256, H=2, D=64,
-                                                          mask=16, kind=0, base=4, mode=0, share_p=0, scale=0.125,
-                                                          dtype=0, variant=0, stream=None), **kw}[n] for n in
-                                                  ("q", "k", "v", "o", "n_obj", "frames", "pixels", "H", "D", "mask", "kind",
-                                                   "base", "mode", "share_p", "scale", "dtype", "variant", "stream")])
+    inj = lambda **kw: lib.mvoc_attn_inject_fwd(*[{**dict(q=16, k=16, v=16, o=16, ldq=128, ldk=128, ldv=128, ldo=128,
+                                                          n_obj=2, frames=2, pixels=256, H=2, D=64, mask=16, kind=0,
+                                                          base=4, mode=0, share_p=0, scale=0.125, dtype=0, variant=0,
+                                                          stream=None), **kw}[n] for n in
+                                                  ("q", "k", "v", "o", "ldq", "ldk", "ldv", "ldo", "n_obj", "frames",
+                                                   "pixels", "H", "D", "mask", "kind", "base", "mode", "share_p", "scale",
+                                                   "dtype", "variant", "stream")])
     assert inj(q=None) == -1 and b"null pointer" in lib.mvoc_last_error()
     assert inj(n_obj=0) == -1 and b"n_obj" in lib.mvoc_last_error()
     assert inj(mode=2) == -1 and b"mode" in lib.mvoc_last_error()
-    assert inj(share_p=1) == -2 and b"share_p" in lib.mvoc_last_error()
+    assert inj(mode=1, share_p=1) == -2 and b"share_p" in lib.mvoc_last_error()     # temporal kernel is HBM-bound
+    assert inj(ldq=100) == -1 and b"row stride" in lib.mvoc_last_error()
+    rc = lib.mvoc_attn_pair_fwd(16, 16, 16, 16, 1, 1, 128, 128, 64, *([0] * 12), 0, 0.125, 0, 0, None)
+    assert rc == -1 and b"pair_batches" in lib.mvoc_last_error()
+    # the tcgen05 GEMM family validates shapes before touching the device
+    rc = lib.mvoc_linear(16, 16, None, None, 16, 128, 100, 64, 100, 0, 64, 0, 0, None)
+    assert rc == -2 and b"K=100" in lib.mvoc_last_error()
+    rc = lib.mvoc_linear(16, 16, None, None, 16, 128, 64, 64, 32, 0, 64, 0, 0, None)
+    assert rc == -1 and b"leading dimensions" in lib.mvoc_last_error()
+    rc = lib.mvoc_conv3x3_nhwc(16, 16, None, None, None, None, 0, 16, 1, 8, 8, 48, 64, 0, 0, None)
+    assert rc == -2 and b"multiple of 64" in lib.mvoc_last_error()
+    rc = lib.mvoc_conv3x3_nhwc(16, 16, None, None, 16, None, 64, 16, 1, 8, 8, 64, 64, 0, 0, None)
+    assert rc == -1 and b"x2 and w2" in lib.mvoc_last_error()
+    rc = lib.mvoc_temporal_conv3(16, 16, None, None, 16, 1, 0, 64, 64, 64, 0, 0, None)
+    assert rc == -1 and b"empty problem" in lib.mvoc_last_error()
+    rc = lib.mvoc_linear_geglu(16, 16, None, 16, 128, 64, 96, 0, 0, None)
+    assert rc == -2 and b"multiple of 64" in lib.mvoc_last_error()
+    rc = lib.mvoc_linear(16, 16, None, None, 16, 128, 64, 64, 64, 0, 64, 2, 0, None)
+    assert rc == -2 and b"dtype" in lib.mvoc_last_error()                           # fp32 storage is not supported
 
 
 def test_product_ops_refuse_cpu_tensors():

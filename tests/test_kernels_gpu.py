@@ -72,6 +72,46 @@ def test_attention_vs_oracle(cuda_device, B, H, Nq, Nk, variant):
     assert err <= 1e-2, f"rel L2 {err:.3e} (variant {variant})"
 
 
+@pytest.mark.parametrize("B,H,Nq,Nk", [(2, 5, 256, 256), (2, 5, 256, 145), (1, 3, 200, 77), (1, 5, 4096, 4096)])
+def test_attention_fp16_vs_oracle(cuda_device, B, H, Nq, Nk):
+    """fp16 storage (the reference's dtype on GPU, composite.py:76-77): same kernel, fp16 operand formats."""
+    from mvoc_b200 import ops
+
+    torch.manual_seed(B * 1000 + Nq + Nk)
+    C = H * 64
+    q, k, v = torch.randn(B, Nq, C).half(), torch.randn(B, Nk, C).half(), torch.randn(B, Nk, C).half()
+    ref = ops_ref.sdpa_ref(q.float(), k.float(), v.float(), H)
+    out = ops.attention(q.to(cuda_device), k.to(cuda_device), v.to(cuda_device), H)
+    torch.cuda.synchronize()
+    assert out.dtype == torch.float16 and torch.isfinite(out.float()).all()
+    err = rel_l2(out, ref)
+    assert err <= 3e-3, f"rel L2 {err:.3e}"     # fp16 P carries 3 more mantissa bits than bf16 P
+
+
+@pytest.mark.parametrize("variant", [2, 4])
+@pytest.mark.parametrize("B,H,N,pair,dtype", [(4, 2, 256, 4, torch.bfloat16), (2, 5, 1024, 2, torch.bfloat16),
+                                              (3, 1, 200, 3, torch.bfloat16), (1, 5, 4096, 1, torch.bfloat16),
+                                              (2, 2, 320, 2, torch.float16)])
+def test_attention_pair_vs_oracle(cuda_device, B, H, N, pair, dtype, variant):
+    """One softmax, two P.V products (mvoc_attn_pair_fwd): both outputs against the fp32 oracle, and the first
+    output against the plain kernel (same math, 64-key instead of 128-key blocks)."""
+    from mvoc_b200 import ops
+
+    torch.manual_seed(N + B)
+    C = H * 64
+    q, k = torch.randn(B, N, C).to(dtype), torch.randn(B, N, C).to(dtype)
+    v = torch.randn(B + pair, N, C).to(dtype)
+    qd, kd, vd = q.to(cuda_device), k.to(cuda_device), v.to(cuda_device)
+    out = ops.attention_pair(qd, kd, vd, H, pair, variant=variant)
+    torch.cuda.synchronize()
+    ref0 = ops_ref.sdpa_ref(q.float(), k.float(), v[:B].float(), H)
+    ref1 = ops_ref.sdpa_ref(q.float(), k.float(), v[pair:].float(), H)
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out[:B], ref0) <= 1e-2 and rel_l2(out[pair:], ref1) <= 1e-2
+    plain = ops.attention(qd, kd, vd[:B].contiguous(), H, variant=variant)
+    assert rel_l2(out[:B], plain.float()) <= 5e-3
+
+
 def test_attention_large_logits_and_strided(cuda_device):
     """Peaked softmax (exercises the lazy O rescale) on q/k/v that are slices of one fused buffer."""
     from mvoc_b200 import ops
@@ -422,3 +462,139 @@ def test_layernorm_vs_torch(cuda_device, M, C):
     assert rel_l2(out, ref) <= 3e-3
     again = ops.layernorm(x.to(cuda_device), w.to(cuda_device), b.to(cuda_device), 1e-5)
     assert torch.equal(out, again)
+
+
+# ------------------------------------------------------------------ dense work on tcgen05 (csrc/gemm_tc.cu)
+GEMM_VARIANTS = [0, 1]      # one CTA per tile / CTA pairs (cta_group::2)
+
+
+@pytest.mark.parametrize("variant", GEMM_VARIANTS)
+@pytest.mark.parametrize("M,K,N,mode", [(128, 64, 64, 0), (1000, 320, 320, 2), (4096, 320, 960, 0), (777, 640, 640, 2),
+                                        (2048, 1280, 1280, 1), (11600, 1024, 640, 0), (300, 128, 192, 2),
+                                        (5000, 320, 1280, 2)])
+def test_linear_vs_torch(cuda_device, M, K, N, mode, variant):
+    """mvoc_linear: x @ w^T (+ bias) (+ residual), single rounding of the fp32 accumulator."""
+    from mvoc_b200 import ops
+
+    torch.manual_seed(M + K + N)
+    x = torch.randn(M, K).bfloat16()
+    w = (torch.randn(N, K) * K ** -0.5).bfloat16()
+    b = torch.randn(N).bfloat16() if mode >= 1 else None
+    r = torch.randn(M, N).bfloat16() if mode >= 2 else None
+    ref = x.float() @ w.float().t()
+    if b is not None:
+        ref = ref + b.float()
+    if r is not None:
+        ref = ref + r.float()
+    d = lambda t: None if t is None else t.to(cuda_device)
+    out = ops.linear(d(x), d(w), d(b), d(r), variant=variant)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) <= 3e-3
+
+
+@pytest.mark.parametrize("variant", GEMM_VARIANTS)
+def test_linear_strided_views(cuda_device, variant):
+    """x and out as column slices of wider buffers (row strides ldx / ldo), residual with its own stride."""
+    from mvoc_b200 import ops
+
+    torch.manual_seed(3)
+    M, K, N = 640, 128, 192
+    xb = torch.randn(M, K + 64, device=cuda_device).bfloat16()
+    ob = torch.zeros(M, N + 128, device=cuda_device).bfloat16()
+    rb = torch.randn(M, N + 64, device=cuda_device).bfloat16()
+    w = (torch.randn(N, K, device=cuda_device) * K ** -0.5).bfloat16()
+    x, out, r = xb[:, :K], ob[:, 64:64 + N], rb[:, :N]
+    ops.linear(x, w, None, r, out=out, variant=variant)
+    torch.cuda.synchronize()
+    ref = x.float() @ w.float().t() + r.float()
+    assert rel_l2(out, ref) <= 3e-3
+    assert float(ob[:, :64].abs().max()) == 0.0 and float(ob[:, 64 + N:].abs().max()) == 0.0   # nothing outside
+
+
+@pytest.mark.parametrize("variant", GEMM_VARIANTS)
+@pytest.mark.parametrize("N,H,W,ci,co,ci2,res", [(2, 64, 64, 64, 64, 0, False), (4, 32, 32, 128, 128, 0, True),
+                                                 (3, 16, 16, 64, 320, 0, True), (2, 11, 20, 64, 64, 0, False),
+                                                 (5, 8, 8, 64, 320, 128, False), (5, 16, 16, 128, 640, 64, True),
+                                                 (2, 64, 64, 320, 320, 0, True)])
+def test_conv3x3_vs_torch(cuda_device, N, H, W, ci, co, ci2, res, variant):
+    """mvoc_conv3x3_nhwc (+ fused 1x1 shortcut source, + residual) against torch conv2d in fp32."""
+    import torch.nn.functional as F
+
+    from mvoc_b200 import ops
+
+    torch.manual_seed(N * H + ci + co)
+    x = torch.randn(N, H, W, ci).bfloat16()
+    w = (torch.randn(co, ci, 3, 3) * (9 * ci) ** -0.5).bfloat16()
+    b = torch.randn(co).bfloat16()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=1).permute(0, 2, 3, 1)
+    x2 = w2 = r = None
+    if ci2:
+        x2 = torch.randn(N, H, W, ci2).bfloat16()
+        w2 = (torch.randn(co, ci2) * ci2 ** -0.5).bfloat16()
+        ref = ref + x2.float() @ w2.float().t()
+    if res:
+        r = torch.randn(N, H, W, co).bfloat16()
+        ref = ref + r.float()
+    d = lambda t: None if t is None else t.to(cuda_device)
+    out = ops.conv3x3(d(x), ops.conv_taps(d(w)), d(b), d(r), d(x2), d(w2), variant=variant)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) <= 3e-3
+
+
+@pytest.mark.parametrize("variant", GEMM_VARIANTS)
+@pytest.mark.parametrize("B,T,S,ci,co,res", [(2, 16, 256, 64, 64, False), (5, 16, 64, 128, 128, True),
+                                             (3, 8, 100, 64, 192, True), (5, 32, 8, 64, 64, False),
+                                             (1, 1, 256, 64, 64, False), (5, 2, 4096, 64, 64, True)])
+def test_temporal_conv3_vs_torch(cuda_device, B, T, S, ci, co, res, variant):
+    """mvoc_temporal_conv3 against torch Conv3d (3,1,1) with zero padding at the ends of each video."""
+    import torch.nn.functional as F
+
+    from mvoc_b200 import ops
+
+    torch.manual_seed(B * T + S)
+    x = torch.randn(B * T, S, ci).bfloat16()
+    w = (torch.randn(co, ci, 3, 1, 1) * (3 * ci) ** -0.5).bfloat16()
+    b = torch.randn(co).bfloat16()
+    x5 = x.float().view(B, T, S, ci).permute(0, 3, 1, 2)[..., None]                    # [B, ci, T, S, 1]
+    ref = F.conv3d(x5, w.float(), b.float(), padding=(1, 0, 0))[..., 0].permute(0, 2, 3, 1).reshape(B * T, S, co)
+    r = None
+    if res:
+        r = torch.randn(B * T, S, co).bfloat16()
+        ref = ref + r.float()
+    d = lambda t: None if t is None else t.to(cuda_device)
+    out = ops.temporal_conv3(d(x), ops.conv_taps(d(w)), d(b), B, T, d(r), variant=variant)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) <= 3e-3
+
+
+@pytest.mark.parametrize("variant", GEMM_VARIANTS)
+@pytest.mark.parametrize("M,K,F", [(256, 64, 64), (1000, 320, 1280), (4096, 640, 2560), (300, 128, 192)])
+def test_linear_geglu_vs_torch(cuda_device, M, K, F, variant):
+    """GEGLU projection with the gate in the GEMM epilogue against Linear -> chunk -> value * gelu(gate) in fp32."""
+    import torch.nn.functional as Fn
+
+    from mvoc_b200 import ops
+
+    torch.manual_seed(M + F)
+    x = torch.randn(M, K).bfloat16()
+    w = (torch.randn(2 * F, K) * K ** -0.5).bfloat16()
+    b = torch.randn(2 * F).bfloat16()
+    val, gate = (x.float() @ w.float().t() + b.float()).chunk(2, dim=-1)
+    ref = val * Fn.gelu(gate)
+    out = ops.linear_geglu(x.to(cuda_device), w.to(cuda_device), b.to(cuda_device), variant=variant)
+    torch.cuda.synchronize()
+    assert rel_l2(out, ref) <= 3e-3
+
+
+def test_dense_fp16_storage(cuda_device):
+    """fp16 activations / weights through the same kernels (the reference's GPU dtype)."""
+    from mvoc_b200 import ops
+
+    torch.manual_seed(5)
+    x = torch.randn(512, 128).half()
+    w = (torch.randn(256, 128) * 128 ** -0.5).half()
+    b = torch.randn(256).half()
+    out = ops.linear(x.to(cuda_device), w.to(cuda_device), b.to(cuda_device))
+    torch.cuda.synchronize()
+    assert out.dtype == torch.float16
+    assert rel_l2(out, x.float() @ w.float().t() + b.float()) <= 1e-3

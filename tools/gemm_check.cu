@@ -183,6 +183,12 @@ static double checked_err(int rc, const bf16* y, const float* ref, size_t n) {
     return rel_l2(y, ref, n);
 }
 
+static bf16* g_flush = nullptr;
+static void flush_l2() {   // 256 MB write: larger than the 126 MB L2
+    if (!g_flush) CK(cudaMalloc(&g_flush, (size_t)256 << 20));
+    CK(cudaMemsetAsync(g_flush, 0, (size_t)256 << 20));
+}
+
 // ------------------------------------------------------------------ sections
 static int section_linear(int variant) {
     // M, K, N, ldx pad, ldo pad, BN override
@@ -298,11 +304,6 @@ static int section_geglu(int variant) {
     return bad;
 }
 
-static bf16* g_flush = nullptr;
-static void flush_l2() {   // 256 MB write: larger than the 126 MB L2
-    if (!g_flush) CK(cudaMalloc(&g_flush, (size_t)256 << 20));
-    CK(cudaMemsetAsync(g_flush, 0, (size_t)256 << 20));
-}
 template <typename Fn> static float time_ms(Fn fn, int iters) {
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a));
@@ -406,8 +407,42 @@ static int section_time(int variant) {
     return e == cudaSuccess ? 0 : 1;
 }
 
+// one <linear|conv> <variant> ...: a single shape launched a few times (the target of an ncu capture)
+//   one linear <variant> M K N res        |   one conv <variant> N H W Cin Cout
+static int section_one(int argc, char** argv) {
+    if (argc < 4) return 1;
+    const int variant = atoi(argv[3]);
+    if (!strcmp(argv[2], "linear") && argc >= 8) {
+        const int64_t M = atoll(argv[4]);
+        const int K = atoi(argv[5]), N = atoi(argv[6]), res = atoi(argv[7]);
+        bf16 *x = dev_random((size_t)M * K, 1.0f), *w = dev_random((size_t)N * K, 0.05f), *bias = dev_random(N, 1.0f),
+             *r = res ? dev_random((size_t)M * N, 1.0f) : nullptr, *y = dev_alloc<bf16>((size_t)M * N);
+        for (int i = 0; i < 4; ++i) {
+            flush_l2();
+            const int rc = mvoc_linear(x, w, bias, r, y, M, K, N, K, N, N, MVOC_BF16, variant, nullptr);
+            if (rc) printf("rc=%d %s\n", rc, mvoc_last_error());
+        }
+    } else if (!strcmp(argv[2], "conv") && argc >= 9) {
+        const int N = atoi(argv[4]), H = atoi(argv[5]), W = atoi(argv[6]), ci = atoi(argv[7]), co = atoi(argv[8]);
+        const size_t px = (size_t)N * H * W;
+        bf16 *x = dev_random(px * ci, 1.0f), *wt = dev_random((size_t)9 * co * ci, 0.02f), *bias = dev_random(co, 1.0f),
+             *y = dev_alloc<bf16>(px * co);
+        for (int i = 0; i < 4; ++i) {
+            flush_l2();
+            const int rc = mvoc_conv3x3_nhwc(x, wt, bias, nullptr, nullptr, nullptr, 0, y, N, H, W, ci, co, MVOC_BF16, variant, nullptr);
+            if (rc) printf("rc=%d %s\n", rc, mvoc_last_error());
+        }
+    } else {
+        return 1;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    printf("one: %s\n", cudaGetErrorString(e));
+    return e == cudaSuccess ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
     const char* what = argc > 1 ? argv[1] : "linear";
+    if (!strcmp(what, "one")) return section_one(argc, argv);
     const int variant = argc > 2 ? atoi(argv[2]) : 0;
     int rc = mvoc_device_check(0);
     if (rc != 0) {

@@ -170,6 +170,31 @@ def section_time():
     print(f"  feature_blend l0: {t:.4f} ms  {by / t / 1e6:.0f} GB/s (min bytes)")
 
 
+def section_pair():
+    """Injected l0 / l1 spatial self-attention: all 5 branches through the plain kernel vs sources plain + the
+    uncond / cond pair through the one-softmax pair kernel (what mvoc_attn_inject_fwd does with share_p)."""
+    import torch
+
+    from mvoc_b200 import ops
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    for (T, H, N) in [(16, 5, 4096), (16, 10, 1024), (16, 20, 256)]:
+        C = H * 64
+        nb = 5
+        q = torch.randn(nb * T, N, C, device=dev).bfloat16()
+        k = torch.randn(nb * T, N, C, device=dev).bfloat16()
+        v = torch.randn(nb * T, N, C, device=dev).bfloat16()
+        fl = 4.0 * nb * T * H * N * N * 64
+        t_all = _time_cuda(lambda: ops.attention(q, k, v, H), iters=5)
+        t_src = _time_cuda(lambda: ops.attention(q[:3 * T], k[:3 * T], v[:3 * T], H), iters=5)
+        t_pair = _time_cuda(lambda: ops.attention_pair(q[3 * T:4 * T], k[3 * T:4 * T], v[3 * T:], H, T), iters=5)
+        t_two = _time_cuda(lambda: ops.attention(q[3 * T:], k[3 * T:], v[3 * T:], H), iters=5)
+        print(f"  T={T} H={H} N={N}: all-plain {t_all:.3f} ms ({fl / t_all / 1e9:.0f} TF/s) | sources {t_src:.3f} + pair "
+              f"{t_pair:.3f} = {t_src + t_pair:.3f} ms ({fl / (t_src + t_pair) / 1e9:.0f} TF/s of reference FLOPs); "
+              f"the pair as two plain branches: {t_two:.3f} ms")
+
+
 def section_dense():
     """The tcgen05 GEMM family (csrc/gemm_tc.cu) against the libraries it replaces, on the UNet's shapes."""
     import torch
@@ -239,6 +264,8 @@ if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what == "dense":
         section_dense()
+    if what == "pair":
+        section_pair()
     if what in ("attn", "all"):
         section_attn()
     if what in ("time", "all"):
