@@ -86,6 +86,8 @@ struct Params {
     int8_t off[2][MAX_TAPS][3];   // coordinate shift of (d1, d2, d3) per tap
     int gate_off;              // GEGLU: row of W where the gate half starts (F)
     int has_res;
+    int dbg;                   // timing experiments only (results are garbage): 1 = never reload the weight stage,
+                               // 2 = never reload the activation stage (variant bits 20, 21)
     const void* bias;          // [N] (GEGLU: [2F]) in the activation dtype, or nullptr
 };
 
@@ -298,10 +300,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                             ptx::mbar_wait(b_empty + 8 * s, ph ^ 1u, 1);
                             const uint32_t sA = sStage + s * C::STAGE_BYTES, sB = sA + A_BYTES;
                             const uint32_t full = b_full + 8 * s;
-                            if (!C::kTwoCta) ptx::mbar_expect_tx(full, C::STAGE_BYTES);
-                            else if (leader) ptx::mbar_expect_tx(full, 2 * C::STAGE_BYTES);
-                            tma_load_tile<C::kTwoCta>(sA, ma, full, kc * KC, tc.c1 + prm.off[src][tap][0],
-                                                      tc.c2 + prm.off[src][tap][1], tc.c3 + prm.off[src][tap][2]);
+                            const bool skip_w = (prm.dbg & 1) && it >= (uint32_t)kStages;
+                            const bool skip_a = (prm.dbg & 2) && it >= (uint32_t)kStages;
+                            const uint32_t bytes = (skip_a ? 0 : A_BYTES) + (skip_w ? 0 : C::B_BYTES);
+                            if (!C::kTwoCta) ptx::mbar_expect_tx(full, bytes);
+                            else if (leader) ptx::mbar_expect_tx(full, 2 * bytes);
+                            if (!skip_a)
+                                tma_load_tile<C::kTwoCta>(sA, ma, full, kc * KC, tc.c1 + prm.off[src][tap][0],
+                                                          tc.c2 + prm.off[src][tap][1], tc.c3 + prm.off[src][tap][2]);
+                            if (skip_w) continue;
                             if (C::kEpi == EPI_GEGLU) {
                                 // accumulator columns = NP value columns then NP gate columns of the same Linear
                                 constexpr int NP = C::BN / 2;
@@ -688,6 +695,7 @@ static int run(const Problem& pb, cudaStream_t stream) {
     prm.bias = pb.bias;
     prm.has_res = pb.residual != nullptr;
     prm.gate_off = (int)pb.N;
+    prm.dbg = (pb.variant >> 20) & 3;
     int BN = (pb.variant >> 8) & 0x1ff;
     if (pb.geglu) {
         if (BN == 0) BN = pb.N % 128 == 0 ? 256 : 128;

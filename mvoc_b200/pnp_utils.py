@@ -29,6 +29,7 @@ from . import ops
 from .unet3d import AttnProcessor2_0
 
 MaskPair = Tuple[torch.Tensor, torch.Tensor]
+SHARE_P_MIN_TOKENS = 2048      # spatial layers at least this long run the composite pair through the pair kernel
 
 
 # --------------------------------------------------------------------------
@@ -181,10 +182,13 @@ class _InjectingProcessor(AttnProcessor2_0):
         else:
             frm = par.frame_range(n_frames_total) if par is not None else None
             tokens = _MASKS.tokens(mask, height, width, soft=False, frames=frm)  # binary mask (:648)
-        # blend (:628-672 / :782-850) + attention of every branch (:684 / :862) in one C-ABI call; on the spatial
-        # layers the uncond / cond pair shares one softmax (they receive the same Q', K': :664-668)
+        # blend (:628-672 / :782-850) + attention of every branch (:684 / :862) in one C-ABI call; on the large
+        # spatial layers the uncond / cond pair shares one softmax (they receive the same Q', K': :664-668).  Measured
+        # on B200 (profiles/r02_attn_pair.txt): 2.06 -> 1.91 ms per layer at 4096 tokens, a loss below 2048 tokens
+        # (64-key blocks and a second launch cost more than the saved exponentials there).
+        share_p = (not self.temporal) and hidden_states.shape[1] >= SHARE_P_MIN_TOKENS
         out = ops.attention_inject_(q, k, v, tokens, attn.heads, n_obj, frames, bool(self.inject_background),
-                                    self.temporal)
+                                    self.temporal, share_p=share_p)
         return attn.out_proj(out)                                               # :692 (+ the block's skip add)
 
 

@@ -324,6 +324,29 @@ template <typename Fn> static float time_ms(Fn fn, int iters) {
     return total / iters;
 }
 
+// shared-memory-port experiment: the same convolutions with the weight and / or activation stages never reloaded
+// (variant bits 20 / 21; results are garbage, only the time matters).  If the MMA rate rises when the TMA fill
+// traffic disappears, the SM's shared-memory port (TMA writes + MMA operand reads) is what bounds the kernel.
+static int section_port(int variant) {
+    const int convs[][5] = {{80, 64, 64, 960, 320}, {80, 32, 32, 1280, 640}, {80, 16, 16, 1280, 1280}};
+    for (auto& c : convs) {
+        const int N = c[0], Hh = c[1], W = c[2], ci = c[3], co = c[4];
+        const size_t px = (size_t)N * Hh * W;
+        bf16 *x = dev_random(px * ci, 1.0f), *wt = dev_random((size_t)9 * co * ci, 0.02f), *bias = dev_random(co, 1.0f),
+             *y = dev_alloc<bf16>(px * co);
+        const double fl = 2.0 * px * co * (double)ci * 9;
+        for (int dbg = 0; dbg < 4; ++dbg) {
+            const int v = variant | (dbg << 20);
+            const float t = time_ms([&] { mvoc_conv3x3_nhwc(x, wt, bias, nullptr, nullptr, nullptr, 0, y, N, Hh, W, ci, co, MVOC_BF16, v, nullptr); }, 5);
+            printf("conv %dx%dx%d %4d->%4d v%d reload %s%s: %.3f ms  %.0f TF/s\n", N, Hh, W, ci, co, variant,
+                   (dbg & 2) ? "-" : "A", (dbg & 1) ? "-" : "W", t, fl / t / 1e9);
+            fflush(stdout);
+        }
+        cudaFree(x), cudaFree(wt), cudaFree(bias), cudaFree(y);
+    }
+    return 0;
+}
+
 static int section_time(int variant) {
     // the UNet's shapes at config 2 (80 frames): l0 64x64 C320, l1 32x32 C640, l2 16x16 C1280, l3 8x8 C1280
     const int convs[][5] = {{80, 64, 64, 320, 320},   {80, 64, 64, 640, 320},   {80, 64, 64, 960, 320},  {80, 32, 32, 640, 640},
@@ -455,6 +478,7 @@ int main(int argc, char** argv) {
     else if (!strcmp(what, "tconv")) bad = section_tconv(variant);
     else if (!strcmp(what, "geglu")) bad = section_geglu(variant);
     else if (!strcmp(what, "time")) bad = section_time(variant);
+    else if (!strcmp(what, "port")) bad = section_port(variant);
     else {
         printf("usage: gemm_check linear|conv|tconv|geglu|time [variant]\n");
         return 2;
