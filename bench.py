@@ -28,6 +28,30 @@ sys.path.insert(0, ROOT)
 
 METRIC = "video frames/s, 50-step 16x512^2 bg+2obj composite"
 UNIT = "frames/s"
+PARITY_BAR = 5e-3      # multi-rank latents vs the single-GPU run after the first steps (relative L2)
+
+
+def ncu_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the l0 attention kernel from the newest committed ncu summary
+    (profiles/*ncu_attn_l0*summary.txt); (None, reason) when there is none.  Never a literal."""
+    import glob
+    import re
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_attn_l0*summary.txt")))
+    for path in reversed(files):
+        rd = wr = None
+        with open(path) as f:
+            for ln in f:
+                m = re.match(r"\s*dram__bytes_(read|write)\.sum\s+([0-9.]+)\s*(\w+)", ln)
+                if m:
+                    val = float(m.group(2)) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(3), 1.0)
+                    if m.group(1) == "read":
+                        rd = val
+                    else:
+                        wr = val
+        if rd is not None and wr is not None:
+            return rd + wr, "ncu --set full dram__bytes_read+write per launch, " + os.path.relpath(path, ROOT)
+    return None, "no ncu summary under profiles/"
 
 
 # --------------------------------------------------------------------------- helpers
@@ -311,6 +335,29 @@ def run_mvoc(args):
     launches = ops.launch_count - launches0
     ms_eager_total = k0.elapsed_time(k1)
 
+    # ---- multi-rank parity (every N > 1 line carries it): the first steps of the sharded run against the same
+    # steps on ONE GPU (rank 0, no partition).  Only the merge order of the GroupNorm statistics differs.
+    parity = None
+    if world > 1:
+        n_par = min(2, K)
+        barrier()
+        lat_multi = loop(0, n_par).clone()
+        barrier()
+        if rank == 0:
+            solo = I2VGenXLPipeline(unet, dev, parallel=FrameParallel.single(dev), use_cuda_graphs=False)
+            solo.scheduler = pipe.scheduler
+            unet.ctx.parallel = None
+            lat_solo = inputs["init_latents"].to(dev).clone()
+            solo.sample_with_pnp_pipeline_with_edit_prompt_extraction_with_attn_injection(
+                cond, lat_solo, banks[0], banks[1:], masks, num_inference_steps=wl.n_steps, guidance_scale=wl.cfg,
+                ddim_init_latents_t_idx=wl.ddim_init_latents_t_idx, fusion_steps=tuple(wl.fusion_step),
+                random_noise_ratio=wl.random_noise_ratio, obj_random_noise_fusion=wl.obj_random_noise_fusion,
+                max_steps=n_par)
+            torch.cuda.synchronize()
+            rel = float((lat_multi - lat_solo).norm() / lat_solo.norm())
+            parity = {"rel_l2_vs_n1": rel, "steps": n_par, "bar": PARITY_BAR, "ok": bool(rel <= PARITY_BAR)}
+        barrier()
+
     if rank != 0:
         _finish(pipe, par)
         return
@@ -320,27 +367,49 @@ def run_mvoc(args):
 
     # ---- roofline of the dominant kernel: l0 spatial self-attention (tcgen05) --------------------
     summ = timer.summary()
-    attn_keys = [k for k in summ if k[0] == "attn"]
+    # spatial / cross attention calls: plain ("attn", B, H, Nq, Nk) and injected ("attn_inject", B, H, Nq, Nk, share_p);
+    # both carry the REFERENCE's FLOPs (every branch its own softmax), whatever the kernels share
+    attn_keys = [k for k in summ if k[0] in ("attn", "attn_inject")]
     attn_ms = sum(summ[k][1] for k in attn_keys)
     attn_flops = sum(summ[k][2] for k in attn_keys)
     tattn_keys = [k for k in summ if k[0] == "attn_temporal"]
-    dom = max(attn_keys, key=lambda k: summ[k][1]) if attn_keys else None
+    shape = lambda k: tuple(k[1:5])
+    by_shape = {}
+    for k in attn_keys:
+        by_shape.setdefault(shape(k), []).append(k)
+    dom_shape = max(by_shape, key=lambda sh: sum(summ[k][1] for k in by_shape[sh])) if by_shape else None
     roof = None
-    if dom is not None:
-        n, ms, work = summ[dom]
+    if dom_shape is not None:
+        ks = by_shape[dom_shape]
+        n = sum(summ[k][0] for k in ks)
+        ms = sum(summ[k][1] for k in ks)
+        work = sum(summ[k][2] for k in ks)
         achieved = work / (ms / 1e3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
+        plain = [k for k in ks if k[0] == "attn"]
+        inj = [k for k in ks if k[0] == "attn_inject"]
+        tfs = lambda kk: (sum(summ[k][2] for k in kk) / (sum(summ[k][1] for k in kk) / 1e3) / 1e12) if kk else None
+        traffic, traffic_src = ncu_traffic_per_launch()
         roof = {
-            "bound": "tensor", "kernel": f"attn_fwd_kernel B={dom[1]} H={dom[2]} Nq={dom[3]} Nk={dom[4]} D=64",
+            "bound": "tensor",
+            "kernel": (f"attn_fwd_kernel: the spatial self-attention layers B={dom_shape[0]} H={dom_shape[1]} "
+                       f"Nq={dom_shape[2]} Nk={dom_shape[3]} D=64 (plain layers: one launch; injected layers: "
+                       "mvoc_attn_inject_fwd = blend + source branches + one-softmax pair kernel for uncond/cond)"),
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "flops": "reference count 4*B*H*Nq*Nk*D per layer for all layers (SURVEY 8d: no discount for shared P)",
             "peak_source": peaks["_source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
             "launches": n, "avg_launch_ms": ms / n, "share_of_step": ms / ms_total,
-            "timing": "CUDA events around each launch while the same K steps are replayed eagerly "
+            "plain_layers": {"calls": sum(summ[k][0] for k in plain), "tflops": tfs(plain),
+                             "frac": (tfs(plain) / peak) if plain else None},
+            "injected_layers": {"calls": sum(summ[k][0] for k in inj), "tflops": tfs(inj),
+                                "frac": (tfs(inj) / peak) if inj else None},
+            "timing": "CUDA events around each C-ABI call while the same K steps are replayed eagerly "
                       "(per-kernel events cannot live inside the captured graphs of the timed region)",
-            "traffic": 820.9e6 if (dom[1], dom[2], dom[3], dom[4]) == (80, 5, 4096, 4096) else None,
-            "traffic_source": "ncu --set full dram__bytes_read+write per launch, profiles/r01_ncu_attn_l0_v3_summary.txt",
+            "traffic": traffic if dom_shape == (80, 5, 4096, 4096) else None,
+            "traffic_source": traffic_src,
         }
     gn_keys = [k for k in summ if k[0] == "groupnorm"]
+    ex_keys = [k for k in summ if k[0] == "exchange"]
     gemm_keys = [k for k in summ if k[0] == "gemm"]
     gemm_ms = sum(summ[k][1] for k in gemm_keys)
     extra = {
@@ -355,6 +424,9 @@ def run_mvoc(args):
         "groupnorm_gbs": (sum(summ[k][2] for k in gn_keys) / (sum(summ[k][1] for k in gn_keys) / 1e3) / 1e9)
         if gn_keys else None,
         "groupnorm_share_of_step": sum(summ[k][1] for k in gn_keys) / ms_total if gn_keys else None,
+        # frame-shard <-> pixel-shard exchange (put kernel + wait) of this rank, per step, in the eager replay
+        "exchange_ms_per_step": (sum(summ[k][1] for k in ex_keys) / K) if ex_keys else None,
+        "exchange_calls_per_step": (sum(summ[k][0] for k in ex_keys) / K) if ex_keys else None,
     }
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
@@ -391,23 +463,36 @@ def run_mvoc(args):
         "clocks": clk,
         "kernels": extra,
     }
+    if parity is not None:
+        line["parity"] = parity
     print(json.dumps(line))
     sys.stdout.flush()
     _finish(pipe, par)
+    if parity is not None and not parity["ok"]:
+        raise SystemExit(f"multi-rank parity failed: rel L2 {parity['rel_l2_vs_n1']:.3e} > {PARITY_BAR}")
 
 
 def _finish(pipe, par):
-    """Leave without running destructors when ranks > 1: captured CUDA graphs hold NCCL kernels, and tearing
-    the communicator / graphs down at interpreter exit can block forever.  Results are already printed."""
+    """Orderly teardown: captured CUDA graphs (they hold collective / exchange kernels) go first, then the peer
+    arenas and the process group.  A watchdog turns a teardown that blocks (round 1 saw NCCL do that at interpreter
+    exit) into a plain exit — the results are already printed."""
+    import gc
+
     import torch
 
-    pipe._graphs.clear()
-    torch.cuda.synchronize()
     sys.stdout.flush()
     sys.stderr.flush()
     if par.world > 1:
+        dog = threading.Timer(45.0, lambda: os._exit(0))
+        dog.daemon = True
+        dog.start()
+    pipe._graphs.clear()
+    pipe._graph_pool = None
+    gc.collect()
+    torch.cuda.synchronize()
+    if par.world > 1:
         par.barrier()
-        os._exit(0)
+        par.shutdown()
 
 
 def main():

@@ -293,6 +293,37 @@ int mvoc_linear_geglu(const void* x, const void* w, const void* bias, void* out,
                       int dtype, int variant, void* stream);
 
 /*
+ * ---- frame-shard <-> pixel-shard exchange over NVLink peer memory (csrc/exchange.cu) ----------------------
+ * The multi-GPU partition keeps T/P frames of every branch on each rank; the temporal operators
+ * (TemporalConvLayer, the temporal transformers: i2vgen-xl/pnp_utils.py:1042-1057, :170-220) need all frames of a
+ * pixel, so the activation is re-laid out around them — what the single-GPU reference expresses as the permutes at
+ * :189, :207-213, :1044-1046, :1055-1057.  Each rank owns an ARENA (cudaMalloc + CUDA IPC handle, opened by every
+ * peer); ranks allocate from their arenas in lockstep, so a destination buffer has the same offset everywhere.
+ * A put kernel reads the local shard once and stores every 16-byte vector at its final position in the destination
+ * rank's buffer (pack + transfer + unpack in one pass), then publishes a per-site epoch in every peer's flag row;
+ * mvoc_exchange_wait spins until all sources have published.  Epochs live in device memory: CUDA-graph safe.
+ * `site`: index of the exchange within one forward (each site owns a flag row), < mvoc_exchange_max_sites().
+ * peer_bases: HOST array of `world` device pointers (the arenas as mapped into THIS process; entry `rank` is the
+ * local arena).  dst_offset: byte offset of the destination buffer inside every arena (>= header bytes).
+ */
+int64_t mvoc_exchange_header_bytes(void);
+int mvoc_exchange_max_sites(void);
+int mvoc_exchange_arena_create(int64_t bytes, void** base, void* ipc_handle64);
+int mvoc_exchange_arena_open(const void* ipc_handle64, void** peer_base);
+int mvoc_exchange_arena_close(void* peer_base);
+int mvoc_exchange_arena_destroy(void* base);
+/* x [b, frames_local, S, C] (this rank's frames) -> every rank d: [b, frames_local * world, S / world, C] */
+int mvoc_exchange_to_pixel_shards(const void* x, void* const* peer_bases, int64_t dst_offset, int rank, int world,
+                                  int b, int frames_local, int64_t S, int C, int dtype, int site, void* stream);
+/* y [b, frames_total, S_local, C] (this rank's pixels) -> every rank d: [b, frames_total / world, S_local * world, C] */
+int mvoc_exchange_to_frame_shards(const void* y, void* const* peer_bases, int64_t dst_offset, int rank, int world,
+                                  int b, int frames_total, int64_t S_local, int C, int dtype, int site, void* stream);
+/* `bytes` of src -> slot `rank` of every rank's [world, bytes] buffer (GroupNorm partial statistics of pixel shards) */
+int mvoc_exchange_allgather(const void* src, int64_t bytes, void* const* peer_bases, int64_t dst_offset, int rank,
+                            int world, int site, void* stream);
+int mvoc_exchange_wait(const void* my_base, int world, int site, void* stream);
+
+/*
  * Latent compositing ("noise fusion") fused with the UNet input concat.
  * Replaces pipelines/pipeline_i2vgen_xl.py:1644-1663 and the torch.cat at
  * :1675-1677.

@@ -90,6 +90,21 @@ SIGNATURES = {
     "mvoc_linear": (
         c_int, [c_void_p] * 5 + [c_int64, c_int, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "mvoc_linear_geglu": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_int, c_int, c_int, c_void_p]),
+    "mvoc_exchange_header_bytes": (c_int64, []),
+    "mvoc_exchange_max_sites": (c_int, []),
+    "mvoc_exchange_arena_create": (c_int, [c_int64, ctypes.POINTER(c_void_p), c_void_p]),
+    "mvoc_exchange_arena_open": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
+    "mvoc_exchange_arena_close": (c_int, [c_void_p]),
+    "mvoc_exchange_arena_destroy": (c_int, [c_void_p]),
+    "mvoc_exchange_to_pixel_shards": (
+        c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int64, c_int, c_int, c_int, c_int, c_int64, c_int, c_int, c_int,
+                c_void_p]),
+    "mvoc_exchange_to_frame_shards": (
+        c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int64, c_int, c_int, c_int, c_int, c_int64, c_int, c_int, c_int,
+                c_void_p]),
+    "mvoc_exchange_allgather": (
+        c_int, [c_void_p, c_int64, ctypes.POINTER(c_void_p), c_int64, c_int, c_int, c_int, c_void_p]),
+    "mvoc_exchange_wait": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "mvoc_latent_composite": (
         c_int,
         [c_void_p] * 5 + [c_int, c_int64, c_int64, c_float, c_int, c_int, c_int, c_int, c_void_p],

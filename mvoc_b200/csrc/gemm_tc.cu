@@ -194,7 +194,8 @@ __device__ __forceinline__ Vec16 ldg16_nc(const void* p) {
 // (|error| <= 1.5e-7, far below the 16-bit rounding of the product): one reciprocal, one exp2, a degree-5 Horner.
 __device__ __forceinline__ float gelu_erf(float x) {
     const float t = fabsf(x) * 0.70710678118654752f;
-    const float k = __frcp_rn(fmaf(0.3275911f, t, 1.0f));
+    float k;   // rcp.approx (1 ulp): the IEEE-rounded reciprocal costs a slow-path call per element
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(k) : "f"(fmaf(0.3275911f, t, 1.0f)));
     float p = fmaf(1.061405429f, k, -1.453152027f);
     p = fmaf(p, k, 1.421413741f);
     p = fmaf(p, k, -0.284496736f);

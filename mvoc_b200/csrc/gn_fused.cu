@@ -67,7 +67,7 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned gen0, unsig
 }
 
 template <typename T>
-__global__ void __launch_bounds__(512) gn_fused_kernel(GNFParams p) {
+__global__ void __launch_bounds__(320, 2) gn_fused_kernel(GNFParams p) {
     // smem: part1[R][C], part2[R][C], s1[C], s2[C], sh[C], stat[G] (float2), gen0
     extern __shared__ float gnf_smem[];
     const int C = p.C, VC = C >> 3, Cg = C / p.G, R = p.R;
@@ -110,12 +110,12 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(GNFParams p) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) a1[e] = a2[e] = 0.0f;
             int64_t t = t0 + r;
-            for (; t + 3 * R < t1; t += 4 * R) {   // four independent 16-byte loads in flight per thread
-                Vec16 v[4];
+            for (; t + 7 * R < t1; t += 8 * R) {   // eight independent 16-byte loads in flight per thread
+                Vec16 v[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = ld_global16(xb + (t + u * R) * C);   // allocating: phase 2 re-reads it from L2
+                for (int u = 0; u < 8; ++u) v[u] = ld_global16(xb + (t + u * R) * C);   // allocating: phase 2 re-reads it from L2
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     float f[8];
                     unpack8<T>(v[u], f);
 #pragma unroll
@@ -230,12 +230,12 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(GNFParams p) {
                 sf[e] = be[e] + (addv[e] - ms.x) * sc[e];
             }
             int64_t t = t0 + r;
-            for (; t + 3 * R < t1; t += 4 * R) {
-                Vec16 v[4];
+            for (; t + 7 * R < t1; t += 8 * R) {
+                Vec16 v[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = ld_stream16(xb + (t + u * R) * C);   // last use of X
+                for (int u = 0; u < 8; ++u) v[u] = ld_stream16(xb + (t + u * R) * C);   // last use of X
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     float f[8];
                     unpack8<T>(v[u], f);
 #pragma unroll
@@ -279,10 +279,10 @@ static int gnf_plan(int64_t N, int64_t S, int C, int G, int frames, GNFGeometry*
     int r = 320 / VC;
     if (r < 1) r = 1;
     if (r > 32) r = 32;
-    while (VC * r > 512 && r > 1) --r;
+    while (VC * r > 320 && r > 1) --r;
     geo->R = r;
     geo->threads = VC * r;
-    MVOC_REQUIRE(geo->threads <= 512, MVOC_ERR_UNSUPPORTED, "%s: C=%d exceeds 4096 channels", what, C);
+    MVOC_REQUIRE(geo->threads <= 320, MVOC_ERR_UNSUPPORTED, "%s: C=%d exceeds 2560 channels", what, C);
     MVOC_REQUIRE(geo->threads >= G && geo->threads >= 32, MVOC_ERR_UNSUPPORTED, "%s: C=%d too small for G=%d", what, C, G);
     geo->smem = ((2 * (size_t)r + 3) * (size_t)C) * sizeof(float) + (size_t)G * sizeof(float2);
     MVOC_REQUIRE(geo->smem <= 96 * 1024, MVOC_ERR_UNSUPPORTED, "%s: C=%d needs %zu B of smem", what, C, geo->smem);

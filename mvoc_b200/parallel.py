@@ -18,12 +18,145 @@ import torch
 import torch.distributed as dist
 
 
+class _RawDeviceMemory:
+    """__cuda_array_interface__ view of a raw device pointer (torch.as_tensor wraps it without copying)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+class PeerExchange:
+    """The frame-shard <-> pixel-shard exchange as one-sided puts over NVLink peer memory (csrc/exchange.cu,
+    include/mvoc_b200.h `mvoc_exchange_*`): every rank owns an arena that all peers map through CUDA IPC; buffers are
+    bump-allocated in lockstep on all ranks (same sizes, same order => same offset everywhere) and the bump pointer
+    and the site counter are reset at the start of every UNet forward, so a forward always uses the same addresses
+    (what a captured CUDA graph needs).  torch.distributed only carries the 64-byte IPC handles at start-up.
+
+    Re-use of the arena between two forwards is safe because every step gathers the noise prediction of all ranks
+    (an NCCL collective on the same stream) after its last exchange: no rank can start the puts of forward k+1
+    before every rank has finished reading the buffers of forward k."""
+
+    def __init__(self, group, world: int, rank: int, device, arena_bytes: int):
+        import ctypes
+
+        from . import _cabi
+
+        self.world, self.rank, self.device = world, rank, torch.device(device)
+        self._lib = _cabi.load()
+        self._ct = ctypes
+        self.header = int(self._lib.mvoc_exchange_header_bytes())
+        self.max_sites = int(self._lib.mvoc_exchange_max_sites())
+        self.bytes = int(arena_bytes)
+        base = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        _cabi.check(self._lib.mvoc_exchange_arena_create(self.bytes, ctypes.byref(base), handle),
+                    "mvoc_exchange_arena_create")
+        self.base = base.value
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self.peer_bases = (ctypes.c_void_p * world)()
+        self._opened = []
+        for r in range(world):
+            if r == rank:
+                self.peer_bases[r] = self.base
+                continue
+            p = ctypes.c_void_p()
+            _cabi.check(self._lib.mvoc_exchange_arena_open(ctypes.create_string_buffer(handles[r], 64), ctypes.byref(p)),
+                        "mvoc_exchange_arena_open")
+            self.peer_bases[r] = p.value
+            self._opened.append(p.value)
+        self._mem = torch.as_tensor(_RawDeviceMemory(self.base, self.bytes), device=self.device)
+        self.reset()
+        dist.barrier(group=group)      # every arena is mapped everywhere before the first put
+
+    def reset(self) -> None:
+        """Start of a UNet forward: the same allocation sequence yields the same offsets and sites."""
+        self._cursor = self.header
+        self._site = 0
+
+    def _alloc(self, shape, dtype):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = n * torch.empty(0, dtype=dtype).element_size()
+        off = self._cursor
+        self._cursor = (off + nbytes + 255) // 256 * 256
+        if self._cursor > self.bytes:
+            raise MemoryError(f"exchange arena of {self.bytes >> 20} MiB exhausted (MVOC_EXCHANGE_ARENA_MB)")
+        return off, self._mem[off:off + nbytes].view(dtype).view(*shape)
+
+    def _next_site(self) -> int:
+        s = self._site
+        self._site += 1
+        if s >= self.max_sites:
+            raise RuntimeError(f"more than {self.max_sites} exchanges in one forward")
+        return s
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream().cuda_stream
+
+    def to_pixel_shards(self, x: torch.Tensor, b: int, tl: int, S: int, C: int) -> torch.Tensor:
+        """x contiguous [b*tl, ..., C] (this rank's frames) -> [b*T, 1, S/P, C] (all frames, this rank's pixels)."""
+        from . import _cabi, ops
+
+        P = self.world
+        off, out = self._alloc((b * tl * P, 1, S // P, C), x.dtype)
+        site = self._next_site()
+        with ops._Timed(("exchange", "to_pixel", b * tl, S, C), 2.0 * x.numel() * x.element_size()):
+            _cabi.check(self._lib.mvoc_exchange_to_pixel_shards(x.data_ptr(), self.peer_bases, off, self.rank, P, b, tl,
+                                                                S, C, ops._dt(x), site, self._stream()),
+                        "mvoc_exchange_to_pixel_shards")
+            _cabi.check(self._lib.mvoc_exchange_wait(self.base, P, site, self._stream()), "mvoc_exchange_wait")
+        ops._count(2)
+        return out
+
+    def to_frame_shards(self, y: torch.Tensor, b: int, T: int, sp: int, C: int, h: int, w: int) -> torch.Tensor:
+        """y contiguous [b*T, 1, S/P, C] -> [b*tl, h, w, C] (this rank's frames, all pixels)."""
+        from . import _cabi, ops
+
+        P = self.world
+        off, out = self._alloc((b * (T // P), h, w, C), y.dtype)
+        site = self._next_site()
+        with ops._Timed(("exchange", "to_frame", b * T, sp, C), 2.0 * y.numel() * y.element_size()):
+            _cabi.check(self._lib.mvoc_exchange_to_frame_shards(y.data_ptr(), self.peer_bases, off, self.rank, P, b, T, sp,
+                                                                C, ops._dt(y), site, self._stream()),
+                        "mvoc_exchange_to_frame_shards")
+            _cabi.check(self._lib.mvoc_exchange_wait(self.base, P, site, self._stream()), "mvoc_exchange_wait")
+        ops._count(2)
+        return out
+
+    def allgather(self, t: torch.Tensor) -> torch.Tensor:
+        """[...] fp32 / any dtype, contiguous, a multiple of 16 bytes -> [P, ...] (rank order)."""
+        from . import _cabi, ops
+
+        P = self.world
+        nbytes = t.numel() * t.element_size()
+        off, out = self._alloc((P,) + tuple(t.shape), t.dtype)
+        site = self._next_site()
+        with ops._Timed(("exchange", "allgather", nbytes), float(nbytes) * P):
+            _cabi.check(self._lib.mvoc_exchange_allgather(t.data_ptr(), nbytes, self.peer_bases, off, self.rank, P, site,
+                                                          self._stream()), "mvoc_exchange_allgather")
+            _cabi.check(self._lib.mvoc_exchange_wait(self.base, P, site, self._stream()), "mvoc_exchange_wait")
+        ops._count(2)
+        return out
+
+    def close(self) -> None:
+        for p in self._opened:
+            self._lib.mvoc_exchange_arena_close(p)
+        self._opened = []
+        if self.base:
+            self._mem = None
+            self._lib.mvoc_exchange_arena_destroy(self.base)
+            self.base = None
+
+
 class FrameParallel:
     def __init__(self, group=None, world: int = 1, rank: int = 0, device=None):
         self.group = group
         self.world = world
         self.rank = rank
         self.device = device
+        self.peer: Optional[PeerExchange] = None     # NVLink peer-memory exchange (CUDA devices, world > 1)
 
     # ------------------------------------------------------------------ setup
     @classmethod
@@ -40,14 +173,34 @@ class FrameParallel:
                 backend = "nccl" if (device is not None and torch.device(device).type == "cuda") else "gloo"
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             dist.init_process_group(backend=backend)
-        return cls(dist.group.WORLD, dist.get_world_size(), dist.get_rank(), device)
+        fp = cls(dist.group.WORLD, dist.get_world_size(), dist.get_rank(), device)
+        # MVOC_EXCHANGE=nccl keeps the NCCL all-to-all / all-gather exchange (the A/B baseline of bench.py)
+        if (device is not None and torch.device(device).type == "cuda"
+                and os.environ.get("MVOC_EXCHANGE", "peer") != "nccl"):
+            mb = int(os.environ.get("MVOC_EXCHANGE_ARENA_MB", "6144"))
+            fp.peer = PeerExchange(fp.group, fp.world, fp.rank, device, mb << 20)
+        return fp
+
+    def begin_forward(self) -> None:
+        """Called by the pipeline at the start of every UNet forward."""
+        if self.peer is not None:
+            self.peer.reset()
 
     def shutdown(self) -> None:
+        if self.peer is not None:
+            torch.cuda.synchronize()
+            if dist.is_initialized():
+                dist.barrier(group=self.group)
+            self.peer.close()
+            self.peer = None
         if self.world > 1 and dist.is_initialized():
             dist.destroy_process_group()
 
     def describe(self) -> str:
-        return "single GPU" if self.world == 1 else f"frame-parallel x{self.world} (all-to-all around temporal ops)"
+        if self.world == 1:
+            return "single GPU"
+        how = "NVLink peer-memory puts (mvoc_exchange_*)" if self.peer is not None else "NCCL all-to-all"
+        return f"frame-parallel x{self.world} (re-layout around temporal ops: {how})"
 
     # ------------------------------------------------------------------ plumbing
     def barrier(self) -> None:
@@ -87,6 +240,8 @@ class FrameParallel:
         sp = S // P
         if S % P != 0:
             raise ValueError(f"h*w={S} is not divisible by world_size={P}")
+        if self.peer is not None:
+            return self.peer.to_pixel_shards(x.contiguous(), b, tl, S, C)
         send = x.contiguous().view(b, tl, P, sp, C).permute(2, 0, 1, 3, 4).contiguous()   # [dst, b, tl, sp, C]
         recv = torch.empty_like(send)                                            # [src, b, tl, sp, C]
         dist.all_to_all_single(recv, send, group=self.group)
@@ -97,6 +252,8 @@ class FrameParallel:
         P = self.world
         bT, _, sp, C = y.shape
         b, tl = bT // num_frames, num_frames // P
+        if self.peer is not None:
+            return self.peer.to_frame_shards(y.contiguous(), b, num_frames, sp, C, h, w)
         send = y.contiguous().view(b, P, tl, sp, C).permute(1, 0, 2, 3, 4).contiguous()   # [dst(frame owner), b, tl, sp, C]
         recv = torch.empty_like(send)                                            # [src(pixel owner), b, tl, sp, C]
         dist.all_to_all_single(recv, send, group=self.group)
@@ -105,6 +262,8 @@ class FrameParallel:
     def gather_partials(self, partial: torch.Tensor) -> torch.Tensor:
         """GroupNorm partial statistics of every rank's pixel shard: [N,G,chunks,2] -> [P,N,G,chunks,2]."""
         partial = partial.contiguous()
+        if self.peer is not None and (partial.numel() * partial.element_size()) % 16 == 0:
+            return self.peer.allgather(partial)
         out = torch.empty((self.world * partial.shape[0],) + tuple(partial.shape[1:]), dtype=partial.dtype,
                           device=partial.device)
         dist.all_gather_into_tensor(out, partial, group=self.group)   # concatenated along dim 0

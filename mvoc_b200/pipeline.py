@@ -199,6 +199,7 @@ class I2VGenXLPipeline:
 
     def _unet_body(self, sample, cond, cache, frames):
         unet = self.unet
+        self.parallel.begin_forward()      # peer-memory exchange: same arena offsets / sites in every forward
         b, c, T, h, w = sample.shape
         f0, f1 = frames
         tl = f1 - f0

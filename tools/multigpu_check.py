@@ -48,18 +48,25 @@ def main():
         torch.cuda.synchronize()
         return out
 
+    print(f"[multigpu_check] rank {par.rank}: {par.describe()}", flush=True)
     sharded = run(par)
     par.barrier()
-    sharded_graph = run(par, graphs=True)     # NCCL all-to-alls captured inside the CUDA graphs
+    sharded_graph = run(par, graphs=True)     # the exchange kernels / NCCL collectives captured inside the CUDA graphs
+    par.barrier()
+    # the same partition with the exchange done by NCCL collectives: the peer-memory puts must move the same bytes
+    peer, par.peer = par.peer, None
+    sharded_nccl = run(par) if peer is not None else sharded
+    par.peer = peer
     par.barrier()
     if par.rank == 0:
         single = run(FrameParallel.single(dev))
         err = float((sharded - single).norm() / single.norm())
         same = bool(torch.equal(sharded, sharded_graph))
+        same_nccl = bool(torch.equal(sharded, sharded_nccl))
         print(f"[multigpu_check] {wl_name} x{par.world} ranks, {steps} steps: rel L2 vs single GPU = {err:.3e}; "
-              f"graph replay == eager: {same}")
+              f"graph replay == eager: {same}; peer-memory exchange == NCCL exchange: {same_nccl}")
         assert err <= 1e-2, err
-        assert same
+        assert same and same_nccl
     par.barrier()
     par.shutdown()
 
