@@ -217,19 +217,6 @@ int mvoc_groupnorm_nhwc_apply(const void* x, void* y, const void* gamma, const v
                               int silu, int dtype, void* stream);
 
 /*
- * The same normalisation in ONE launch and TWO DRAM passes (csrc/gn_fused.cu): a persistent, co-resident grid walks
- * the tensor in L2-sized slabs of whole statistics groups — partial statistics, a grid-wide barrier, then the merge
- * and the normalisation of the same tokens, whose second read is served by the 126 MB L2.  The single-GPU product
- * path; pixel shards whose statistics cross GPUs keep the three-launch form above.
- * workspace: mvoc_groupnorm_nhwc_fused_workspace_bytes(N, G) bytes, 256-byte aligned, whose first 256 bytes were
- * zeroed ONCE when the buffer was created (barrier state; the kernel leaves it reusable).  y may alias x.
- */
-int64_t mvoc_groupnorm_nhwc_fused_workspace_bytes(int64_t N, int G);
-int mvoc_groupnorm_nhwc_fused(const void* x, void* y, const void* gamma, const void* beta, const void* add,
-                              int64_t N, int64_t S, int C, int G, int frames_per_stat, float eps, int silu,
-                              int dtype, void* workspace, void* stream);
-
-/*
  * Row-wise LayerNorm over [M, C] (affine, eps): norm1 / norm2 / norm3 of BasicTransformerBlock
  * (i2vgen-xl/pnp_utils.py:249-250, :295-296, :322).  One warp per row, one read + one write.  C % 8 == 0,
  * C <= 2048.  y may alias x.

@@ -52,9 +52,6 @@ SIGNATURES = {
         c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "mvoc_groupnorm_nhwc_apply": (
         c_int, [c_void_p] * 6 + [c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    "mvoc_groupnorm_nhwc_fused_workspace_bytes": (c_int64, [c_int64, c_int]),
-    "mvoc_groupnorm_nhwc_fused": (
-        c_int, [c_void_p] * 5 + [c_int64, c_int64, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p, c_void_p]),
     "mvoc_geglu": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "mvoc_layernorm": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_float, c_int, c_void_p]),
     "mvoc_qk_blend": (

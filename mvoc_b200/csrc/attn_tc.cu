@@ -233,28 +233,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const bool tail = valid < BN;
             ptx::mbar_wait(b_s_full, (uint32_t)j & 1u, 9);
             ptx::tc_fence_after();
-            // One TMEM read of the whole score row (128 fp32 columns -> 128 registers); S is free for the
-            // next Q K^T as soon as it sits in registers, long before the exponentials are done.
+            // The score row moves into registers in 32-column pieces: the row maximum of piece c is computed while
+            // piece c+1 is still streaming out of TMEM.  S is released to the MMA warp (next Q K^T) as soon as the last
+            // piece has landed, long before the exponentials are done.
             uint32_t r[BN];
-#pragma unroll
-            for (int c = 0; c < BN / 32; ++c)
-                ptx::tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
-            ptx::tmem_wait_ld();
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(b_s_free);
-            if (tail) {  // keys past Nk (zero-filled by TMA) must not take part: exp2(-inf) = 0
-#pragma unroll
-                for (int i = 0; i < BN; ++i)
-                    if (i >= valid) r[i] = 0xff800000u;
-            }
-            // row max: four independent chains of 3-input max (FMNMX3)
             float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+            constexpr int NC = BN / 32;
+            ptx::tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+            ptx::tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < BN; i += 8) {
-                mx0 = ptx::max3(mx0, __uint_as_float(r[i + 0]), __uint_as_float(r[i + 1]));
-                mx1 = ptx::max3(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-                mx2 = ptx::max3(mx2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
-                mx3 = ptx::max3(mx3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
+            for (int c = 0; c < NC; ++c) {
+                if (c + 1 < NC) ptx::tmem_ld32(tS + (c + 1) * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[(c + 1) * 32]));
+                if (tail) {  // keys past Nk (zero-filled by TMA) must not take part: exp2(-inf) = 0
+#pragma unroll
+                    for (int i = c * 32; i < c * 32 + 32; ++i)
+                        if (i >= valid) r[i] = 0xff800000u;
+                }
+                // four independent chains of 3-input max (FMNMX3)
+#pragma unroll
+                for (int i = c * 32; i < c * 32 + 32; i += 8) {
+                    mx0 = ptx::max3(mx0, __uint_as_float(r[i + 0]), __uint_as_float(r[i + 1]));
+                    mx1 = ptx::max3(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                    mx2 = ptx::max3(mx2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
+                    mx3 = ptx::max3(mx3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
+                }
+                if (c + 1 < NC) ptx::tmem_wait_ld();
+                if (c + 2 == NC || NC == 1) {   // every piece has left TMEM
+                    ptx::tc_fence_before();
+                    ptx::mbar_arrive(b_s_free);
+                }
             }
             const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
             bool pv_waited = false;

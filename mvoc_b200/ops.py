@@ -483,36 +483,6 @@ def _groupnorm_nhwc_slab(
     return out
 
 
-_gnf_ws: dict = {}
-# MVOC_GN_FUSED=0 keeps the three-launch GroupNorm on a single GPU too (A/B switch, recorded by bench.py)
-_GN_FUSED = os.environ.get("MVOC_GN_FUSED", "1") != "0"
-
-
-def _groupnorm_nhwc_fused(x, weight, bias, groups, eps, silu, frames_per_stat, add, out):
-    """One cooperative launch, two DRAM passes (mvoc_groupnorm_nhwc_fused); single-GPU path."""
-    N, C = x.shape[0], x.shape[-1]
-    S = x.numel() // (N * C)
-    if out is None:
-        out = torch.empty_like(x)
-    if add is not None and (tuple(add.shape) != (N, C) or not add.is_contiguous() or add.dtype != x.dtype):
-        raise ValueError(f"groupnorm_nhwc: add must be contiguous [{N}, {C}] of x's dtype")
-    lib = _cabi.load()
-    need = lib.mvoc_groupnorm_nhwc_fused_workspace_bytes(N, groups)
-    key = x.device.index
-    ws = _gnf_ws.get(key)
-    if ws is None or ws.numel() < need:
-        # zeroed once: the first 256 bytes are the grid barrier's state, which the kernel leaves reusable
-        ws = torch.zeros(max(need, 8 << 20), dtype=torch.uint8, device=x.device)
-        _gnf_ws[key] = ws
-    with _Timed(("groupnorm", N, C, S, frames_per_stat), 2.0 * x.numel() * x.element_size()):
-        rc = lib.mvoc_groupnorm_nhwc_fused(x.data_ptr(), out.data_ptr(), weight.data_ptr(), bias.data_ptr(), _ptr(add),
-                                           N, S, C, groups, frames_per_stat, float(eps), int(bool(silu)), _dt(x),
-                                           ws.data_ptr(), _stream())
-    _cabi.check(rc, "mvoc_groupnorm_nhwc_fused")
-    _count()
-    return out
-
-
 # MVOC_GN_SLAB_MB=<n> (off by default, unmeasured): run the three GroupNorm launches slab by slab, n MB of
 # statistic groups at a time, so that the `apply` pass re-reads a slab that the `stats` pass has just pulled into
 # the 126 MB L2 — two DRAM passes over the tensor instead of three.
@@ -533,11 +503,6 @@ def groupnorm_nhwc(
 ) -> torch.Tensor:
     """GroupNorm(+SiLU) over channels-last x [N, S, C] (or [N, H, W, C]); see _groupnorm_nhwc_slab."""
     N = x.shape[0]
-    if _GN_FUSED and gather is None:
-        _need_cuda(x, weight, bias, add, out)
-        if not x.is_contiguous():
-            raise ValueError("groupnorm_nhwc: x must be contiguous [N, ..., C]")
-        return _groupnorm_nhwc_fused(x, weight, bias, groups, eps, silu, frames_per_stat, add, out)
     if _GN_SLAB_BYTES > 0 and gather is None and N > frames_per_stat and x.is_contiguous():
         group_bytes = frames_per_stat * (x.numel() // N) * x.element_size()    # one statistics group
         step = max(1, _GN_SLAB_BYTES // group_bytes) * frames_per_stat
