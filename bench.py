@@ -126,7 +126,20 @@ def measured_peaks() -> dict:
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "_source": "fallback"}
 
 
+def metric_name(wl) -> str:
+    """BASELINE.json's metric for config 2; the same quantity named after the workload for the other configs."""
+    if wl.name == "config2":
+        return METRIC
+    px = f"{wl.n_frames}x{wl.latent_h * 8}x{wl.latent_w * 8}"
+    if wl.n_obj == 0:
+        return f"video frames/s, {wl.inversion_steps}-step DDIM inversion of {wl.n_videos} x {px} source videos"
+    return f"video frames/s, {wl.n_steps}-step {px} bg+{wl.n_obj}obj composite"
+
+
 def workload_description(wl) -> str:
+    if wl.n_obj == 0:
+        return (f"{wl.name}: full i2vgen-xl UNet random-init, DDIM inversion ({wl.inversion_steps} steps, cfg 1.0, batch 1) "
+                f"of {wl.n_videos} independent source videos of {wl.n_frames} frames x {wl.latent_h}x{wl.latent_w} latents")
     return (f"{wl.name}: full i2vgen-xl UNet random-init, {wl.n_frames} frames x {wl.latent_h}x{wl.latent_w} "
             f"latents, bg+{wl.n_obj} objects, {wl.n_steps}-step DDIM composition, cfg {wl.cfg}, pnp_f_t {wl.pnp_f_t}, "
             f"spatial/temporal attn injection {wl.pnp_spatial_attn_t}/{wl.pnp_temp_attn_t}")
@@ -248,9 +261,13 @@ def run_mvoc(args):
 
     lib = _cabi.load()
     _cabi.check(lib.mvoc_device_check(local), "mvoc_device_check")
+    if synthetic.WORKLOADS[args.workload].n_obj == 0:
+        os.environ["MVOC_EXCHANGE"] = "nccl"      # replicas exchange nothing: no peer arena
     par = FrameParallel.from_env(dev)  # world_size 1 => no-op
 
     wl = synthetic.WORKLOADS[args.workload]
+    if wl.n_obj == 0:
+        return run_inversion(args, wl, par, dev, rank, world, local)
     sched = DDIMSchedule(wl.n_steps)
     inputs = synthetic.make_inputs(wl, sched.timesteps, sched.alphas_cumprod)
     torch.backends.cudnn.benchmark = True
@@ -441,7 +458,7 @@ def run_mvoc(args):
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
 
     line = {
-        "metric": METRIC, "value": frames_per_s, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "metric": metric_name(wl), "value": frames_per_s, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {
@@ -470,6 +487,91 @@ def run_mvoc(args):
     _finish(pipe, par)
     if parity is not None and not parity["ok"]:
         raise SystemExit(f"multi-rank parity failed: rel L2 {parity['rel_l2_vs_n1']:.3e} > {PARITY_BAR}")
+
+
+def run_inversion(args, wl, par, dev, rank, world, local):
+    """BASELINE config 3: group DDIM inversion (pipelines/pipeline_i2vgen_xl.py:1940-2000) of wl.n_videos independent
+    source videos, video v on rank v % N — replicas, no data-path collective (inverse.py processes the entries of
+    group_config.json one after the other).  One step = one inversion step of EVERY video of the group;
+    value = n_videos * n_frames / (inversion_steps * step time)."""
+    import torch
+
+    from mvoc_b200 import ops, synthetic
+    from mvoc_b200.parallel import FrameParallel
+    from mvoc_b200.pipeline import I2VGenXLPipeline
+    from mvoc_b200.unet3d import build_unet
+
+    torch.backends.cudnn.benchmark = True
+    unet = build_unet(wl.unet, seed=0, device=dev)
+    pipe = I2VGenXLPipeline(unet, dev, parallel=FrameParallel.single(dev), use_cuda_graphs=not args.no_graphs)
+    mine = [v for v in range(wl.n_videos) if v % world == rank]
+    bf = lambda x: x.to(device=dev, dtype=torch.bfloat16)
+    vids = []
+    for v in mine:
+        inv = synthetic.make_inversion_inputs(wl, v)
+        vids.append((inv["latents"].to(dev), bf(inv["prompt_embeds"]), bf(inv["image_embeddings"]),
+                     bf(inv["image_latents"]), inv["fps"].to(dev)))
+    K, W = min(args.steps, wl.inversion_steps), max(args.warmup, 0)
+
+    def steps(n, host_io=False):
+        out = None
+        for lat, pe, ie, il, fps in vids:
+            host = torch.empty(lat.shape, dtype=lat.dtype).pin_memory() if host_io else None
+            x = host.copy_(lat.cpu()).to(dev, non_blocking=True) if host_io else lat.clone()
+            saved = pipe.invert(x, pe, ie, il, fps, num_inference_steps=wl.inversion_steps, max_steps=n, keep=False,
+                                on_step=(lambda t, z: host.copy_(z, non_blocking=False)) if host_io else None)
+            out = x
+        return out
+
+    if W > 0:
+        steps(W)
+    torch.cuda.synchronize()
+
+    def barrier():
+        par_all.barrier()
+        torch.cuda.synchronize()
+
+    par_all = par
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ops.launch_count
+    ev0.record()
+    steps(K)
+    ev1.record()
+    barrier()
+    launches = ops.launch_count - l0
+    clk = clocks.stop() if rank == 0 else None
+    ms_step = par_all.max_over_ranks(ev0.elapsed_time(ev1)) / K
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    steps(K, host_io=True)
+    e1.record()
+    barrier()
+    e2e_ms = par_all.max_over_ranks(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)) / K
+    if rank == 0:
+        E = 4 * wl.n_frames * wl.latent_h * wl.latent_w
+        fps_val = wl.n_videos * wl.n_frames / (wl.inversion_steps * ms_step / 1e3)
+        line = {
+            "metric": metric_name(wl), "value": fps_val, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": workload_description(wl),
+                       "parallelism": f"replicas: video v on rank v % {world} (no data-path collective)",
+                       "l2": "activations per step exceed the 126 MB L2; no explicit flush",
+                       "cuda_graphs": bool(pipe.use_cuda_graphs)},
+            "roofline": None, "cpu_baseline": None,
+            "e2e": {"value": wl.n_videos * wl.n_frames / (wl.inversion_steps * e2e_ms / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": len(mine) * E * 4, "ms_per_step": e2e_ms},
+            "gpu_launches": launches, "clocks": clk,
+        }
+        print(json.dumps(line))
+        sys.stdout.flush()
+    _finish(pipe, par)
 
 
 def _finish(pipe, par):

@@ -97,6 +97,16 @@ int mvoc_attn_pair_fwd(const void* q, const void* k, const void* v, void* o,
                        int pair_batches, float scale, int dtype, int variant, void* stream);
 
 /*
+ * Diagnostics: mvoc_attn_fwd (pair_batches == 0) or mvoc_attn_pair_fwd with clock64() time stamps of CTA (0,0,0)
+ * written to trace[key block * 8 + event] (device memory, int64): 0 softmax starts waiting for S, 1 S ready,
+ * 2 row maximum known, 3 exponentials done, 4 P buffer free, 5 P published; 6 Q K^T issued, 7 P V issued.
+ * strides12: the twelve element strides of mvoc_attn_fwd in order.  tools/attn_trace.py prints the phase times.
+ */
+int mvoc_attn_fwd_trace(const void* q, const void* k, const void* v, void* o, int B, int H, int Nq, int Nk, int D,
+                        const int64_t* strides12, int pair_batches, float scale, int dtype, int variant,
+                        long long* trace, void* stream);
+
+/*
  * Short-sequence attention (tokens = frames), one warp per (pixel, head).
  * Replaces F.scaled_dot_product_attention at i2vgen-xl/pnp_utils.py:862-864
  * (injected temporal attn1) and the stock processor on the temporal attn2,

@@ -62,7 +62,13 @@ struct Params {
     int Nq, Nk;
     int pair_batches;   // kNV == 2: the second value / output tensor is this many batches after the first
     float scale_log2;
+    long long* trace;   // diagnostics (mvoc_attn_fwd_trace): clock64() of CTA (0,0,0) at 8 points per key block, or null
 };
+
+// trace slot layout: [block j][event]; events 0-5 by softmax thread 0, 6-7 by the MMA lane
+__device__ __forceinline__ void trace_at(const Params& prm, int j, int ev) {
+    if (prm.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) prm.trace[j * 8 + ev] = clock64();
+}
 
 template <typename T> struct Pack2;
 template <> struct Pack2<__nv_bfloat16> {
@@ -70,11 +76,18 @@ template <> struct Pack2<__nv_bfloat16> {
         __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
         return *reinterpret_cast<uint32_t*>(&b);
     }
+    static __device__ __forceinline__ uint32_t scale(uint32_t v, float f) {   // bf16 = upper half of an fp32
+        return rn(__uint_as_float(v << 16) * f, __uint_as_float(v & 0xffff0000u) * f);
+    }
 };
 template <> struct Pack2<__half> {
     static __device__ __forceinline__ uint32_t rn(float lo, float hi) {
         __half2 b = __floats2half2_rn(lo, hi);
         return *reinterpret_cast<uint32_t*>(&b);
+    }
+    static __device__ __forceinline__ uint32_t scale(uint32_t v, float f) {
+        const float2 x = __half22float2(*reinterpret_cast<__half2*>(&v));
+        return rn(x.x * f, x.y * f);
     }
 };
 // kind::f16 instruction descriptor for 16-bit storage type T (fp16: format 0, bf16: format 1), fp32 accumulation
@@ -198,7 +211,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 ptx::mbar_wait(b_k_full + 8 * s1, (uint32_t)((j + 1) / kStages) & 1u, 5);
                 ptx::mbar_wait(b_s_free, (uint32_t)j & 1u, 6);
                 ptx::tc_fence_after();
-                if (lane == 0) issue_qk(j + 1);
+                if (lane == 0) {
+                    issue_qk(j + 1);
+                    trace_at(prm, j + 1, 6);   // Q K^T of block j+1 issued
+                }
                 __syncwarp();
             }
             ptx::mbar_wait(b_v_full + 8 * s, ph, 7);
@@ -216,6 +232,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 }
                 ptx::tc_commit(b_v_empty + 8 * s);
                 ptx::tc_commit(b_pv_done);
+                trace_at(prm, j, 7);           // P V of block j issued
             }
             __syncwarp();
         }
@@ -228,16 +245,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const uint32_t tS = lane_base + COL_S, tP = lane_base + COL_P, tO = lane_base + COL_O;
         const float sl2 = prm.scale_log2;
         float m_used = -INFINITY, l_sum = 0.0f;
+        bool s_ready = false;   // S of the next block already seen complete by a non-blocking poll
         for (int j = 0; j < n_blocks; ++j) {
             const int valid = min(BN, prm.Nk - j * BN);
             const bool tail = valid < BN;
-            ptx::mbar_wait(b_s_full, (uint32_t)j & 1u, 9);
+            if (threadIdx.x == 0) trace_at(prm, j, 0);   // softmax of block j starts waiting for S
+            if (!s_ready) ptx::mbar_wait(b_s_full, (uint32_t)j & 1u, 9);
             ptx::tc_fence_after();
-            // The score row moves into registers in 32-column pieces: the row maximum of piece c is computed while
-            // piece c+1 is still streaming out of TMEM.  S is released to the MMA warp (next Q K^T) as soon as the last
-            // piece has landed, long before the exponentials are done.
+            if (threadIdx.x == 0) trace_at(prm, j, 1);   // S ready
+            // Online softmax at 32-column granularity.  The score row leaves TMEM in 32-column pieces; piece c+1
+            // streams out while piece c is reduced (its maximum: 16 FMNMX3) and exponentiated, so neither the TMEM
+            // read latency nor a full-row maximum sits in front of the exponentials.  The running stabiliser m_used
+            // only moves when a piece exceeds it by more than 2^8 (rare after the first pieces of a row): then the
+            // running O, l, this block's partial sums and its already packed pieces are rescaled.  S is released to
+            // the MMA warp (next Q K^T) as soon as the last piece has landed.
             uint32_t r[BN];
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+            uint32_t pk[BN / 2];
+            uint64_t la = ptx::pack2(0.0f, 0.0f), lb = la, lc = la, ld = la;
+            const uint64_t sl2_2 = ptx::pack2(sl2, sl2);
+            bool pv_waited = false;            // the previous P V is known complete (blocking wait done)
+            bool pv_ready = (j == 0);          // ... or seen complete by the non-blocking poll
             constexpr int NC = BN / 32;
             ptx::tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
             ptx::tmem_wait_ld();
@@ -249,7 +276,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     for (int i = c * 32; i < c * 32 + 32; ++i)
                         if (i >= valid) r[i] = 0xff800000u;
                 }
-                // four independent chains of 3-input max (FMNMX3)
+                // maximum of the piece: four independent chains of 3-input max (FMNMX3)
+                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
                 for (int i = c * 32; i < c * 32 + 32; i += 8) {
                     mx0 = ptx::max3(mx0, __uint_as_float(r[i + 0]), __uint_as_float(r[i + 1]));
@@ -257,81 +285,88 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     mx2 = ptx::max3(mx2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
                     mx3 = ptx::max3(mx3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
                 }
+                const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+                const bool need = (m_new - m_used) * sl2 > RESCALE_LOG2_THRESHOLD;   // first piece of a row: inf > 8
+                if (__any_sync(0xffffffffu, need)) {
+                    const float f = need ? ptx::ex2_approx((m_used - m_new) * sl2) : 1.0f;   // first piece: 2^-inf = 0
+                    if (need) m_used = m_new;
+                    const uint64_t f2 = ptx::pack2(f, f), z2 = ptx::pack2(0.0f, 0.0f);
+                    l_sum *= f;
+                    la = ptx::fma2(la, f2, z2), lb = ptx::fma2(lb, f2, z2), lc = ptx::fma2(lc, f2, z2), ld = ptx::fma2(ld, f2, z2);
+#pragma unroll
+                    for (int k = 0; k < c * 16; ++k) pk[k] = Pack2<T>::scale(pk[k], f);
+                    if (j > 0) {   // the running O (rare after the first blocks)
+                        if (!pv_waited) {
+                            ptx::mbar_wait(b_pv_done, (uint32_t)(j - 1) & 1u, 10);
+                            ptx::tc_fence_after();
+                            pv_waited = true;
+                        }
+#pragma unroll
+                        for (int oc = 0; oc < kNV * HD / 32; ++oc) {
+                            uint32_t o[32];
+                            ptx::tmem_ld32(tO + oc * 32, o);
+                            ptx::tmem_wait_ld();   // (also completes the score piece in flight)
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                            ptx::tmem_st32(tO + oc * 32, o);
+                        }
+                        ptx::tmem_wait_st();
+                    }
+                }
+                // p = exp2(s * scale*log2e - m * scale*log2e) on pairs (FFMA2); the exponential goes to the MUFU or,
+                // for the pairs selected by kEmuMask, to the FMA-pipe polynomial; packed row sums (FADD2).
+                const uint64_t negm_2 = ptx::pack2(-m_used * sl2, -m_used * sl2);
+#pragma unroll
+                for (int k = c * 16; k < c * 16 + 16; ++k) {
+                    const uint64_t x2 = ptx::fma2(ptx::pack2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1])),
+                                                  sl2_2, negm_2);
+                    float p0, p1;
+                    if ((kEmuMask >> (k & 7)) & 1u) {
+                        ptx::ex2_poly2(x2, p0, p1);
+                    } else {
+                        float x0, x1;
+                        ptx::unpack2(x2, x0, x1);
+                        p0 = ptx::ex2_approx(x0);
+                        p1 = ptx::ex2_approx(x1);
+                    }
+                    const uint64_t p2 = ptx::pack2(p0, p1);
+                    if ((k & 3) == 0) la = ptx::add2(la, p2);
+                    else if ((k & 3) == 1) lb = ptx::add2(lb, p2);
+                    else if ((k & 3) == 2) lc = ptx::add2(lc, p2);
+                    else ld = ptx::add2(ld, p2);
+                    pk[k] = Pack2<T>::rn(p0, p1);
+                }
+                // halfway through: poll (without blocking) whether the previous P V has completed, so that the wait
+                // in front of the P store costs nothing when it has (an mbarrier wait costs ~130 clocks even then)
+                if (c == NC / 2 && !pv_waited && !pv_ready) pv_ready = ptx::mbar_test(b_pv_done, (uint32_t)(j - 1) & 1u);
                 if (c + 1 < NC) ptx::tmem_wait_ld();
                 if (c + 2 == NC || NC == 1) {   // every piece has left TMEM
                     ptx::tc_fence_before();
                     ptx::mbar_arrive(b_s_free);
                 }
             }
-            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-            bool pv_waited = false;
-            if (j == 0) {
-                m_used = mx;
-            } else {
-                const float m_new = fmaxf(m_used, mx);
-                const bool need = (m_new - m_used) * sl2 > RESCALE_LOG2_THRESHOLD;
-                if (__any_sync(0xffffffffu, need)) {
-                    // rescale the running O and l (rare after the first blocks)
-                    ptx::mbar_wait(b_pv_done, (uint32_t)(j - 1) & 1u, 10);
-                    ptx::tc_fence_after();
-                    pv_waited = true;
-                    const float f = need ? ptx::ex2_approx((m_used - m_new) * sl2) : 1.0f;
-                    if (need) m_used = m_new;
-                    l_sum *= f;
-#pragma unroll
-                    for (int c = 0; c < kNV * HD / 32; ++c) {
-                        uint32_t o[32];
-                        ptx::tmem_ld32(tO + c * 32, o);
-                        ptx::tmem_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-                        ptx::tmem_st32(tO + c * 32, o);
-                    }
-                    ptx::tmem_wait_st();
-                }
-            }
-            // p = exp2(s * scale*log2e - m * scale*log2e) on pairs (FFMA2); the exponential goes to the MUFU or,
-            // for the pairs selected by kEmuMask, to the FMA-pipe polynomial; packed row sums (FADD2).
-            const uint64_t sl2_2 = ptx::pack2(sl2, sl2);
-            const uint64_t negm_2 = ptx::pack2(-m_used * sl2, -m_used * sl2);
-            uint32_t pk[BN / 2];
-            uint64_t la = ptx::pack2(0.0f, 0.0f), lb = la, lc = la, ld = la;
-#pragma unroll
-            for (int k = 0; k < BN / 2; ++k) {
-                const uint64_t x2 = ptx::fma2(ptx::pack2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1])),
-                                              sl2_2, negm_2);
-                float p0, p1;
-                if ((kEmuMask >> (k & 7)) & 1u) {
-                    ptx::ex2_poly2(x2, p0, p1);
-                } else {
-                    float x0, x1;
-                    ptx::unpack2(x2, x0, x1);
-                    p0 = ptx::ex2_approx(x0);
-                    p1 = ptx::ex2_approx(x1);
-                }
-                const uint64_t p2 = ptx::pack2(p0, p1);
-                if ((k & 3) == 0) la = ptx::add2(la, p2);
-                else if ((k & 3) == 1) lb = ptx::add2(lb, p2);
-                else if ((k & 3) == 2) lc = ptx::add2(lc, p2);
-                else ld = ptx::add2(ld, p2);
-                pk[k] = Pack2<T>::rn(p0, p1);
-            }
+            if (threadIdx.x == 0) trace_at(prm, j, 2);   // (kept for the trace layout: pieces done)
             {
                 float s0, s1;
                 ptx::unpack2(ptx::add2(ptx::add2(la, lb), ptx::add2(lc, ld)), s0, s1);
                 l_sum += s0 + s1;
             }
+            if (threadIdx.x == 0) trace_at(prm, j, 3);   // exponentials done
             // P buffer is free once the previous P V has completed
-            if (j > 0 && !pv_waited) {
-                ptx::mbar_wait(b_pv_done, (uint32_t)(j - 1) & 1u, 11);
+            if (!pv_waited) {
+                if (!pv_ready) ptx::mbar_wait(b_pv_done, (uint32_t)(j - 1) & 1u, 11);
                 ptx::tc_fence_after();
             }
+            if (threadIdx.x == 0) trace_at(prm, j, 4);   // previous P V complete (P buffer free)
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
                 ptx::tmem_st32(tP + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&pk[c * 32]));
+            // while the P store drains: has the next Q K^T already landed?
+            s_ready = (j + 1 < n_blocks) && ptx::mbar_test(b_s_full, (uint32_t)(j + 1) & 1u);
             ptx::tmem_wait_st();
             ptx::tc_fence_before();
             ptx::mbar_arrive(b_p_full);
+            if (threadIdx.x == 0) trace_at(prm, j, 5);   // P published
         }
         // ---- epilogue: O / l -> 16-bit -> global --------------------------------
         ptx::mbar_wait(b_pv_done, (uint32_t)(n_blocks - 1) & 1u, 12);
@@ -428,7 +463,7 @@ static int launch(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMa
 // Common entry: kNV value tensors per softmax (1 = plain attention, 2 = the uncond/cond pair).
 static int run(const void* q, const void* k, const void* v, void* o, int B, int H, int Nq, int Nk, int D,
                const int64_t (&st)[12], int pair_batches, float scale, int dtype, int variant, void* stream,
-               const char* what) {
+               const char* what, long long* trace = nullptr) {
     MVOC_REQUIRE(q && k && v && o, MVOC_ERR_INVALID_ARG, "%s: null pointer", what);
     MVOC_REQUIRE(dtype == MVOC_BF16 || dtype == MVOC_F16, MVOC_ERR_UNSUPPORTED, "%s: dtype %d unsupported (bf16 / fp16)",
                  what, dtype);
@@ -460,6 +495,7 @@ static int run(const void* q, const void* k, const void* v, void* o, int B, int 
     prm.Nk = Nk;
     prm.pair_batches = pair_batches;
     prm.scale_log2 = scale * 1.4426950408889634f;
+    prm.trace = trace;
     cudaStream_t s = (cudaStream_t)stream;
     // variants (same results up to the exp2 approximation; the tests run all of them):
     //   1, 2: all exponentials on the MUFU;  3 / 4 / 5: 2 / 3 / 4 of every 8 pairs on the FMA-pipe polynomial;  0: default
@@ -505,4 +541,17 @@ extern "C" int mvoc_attn_pair_fwd(const void* q, const void* k, const void* v, v
     MVOC_REQUIRE(pair_batches > 0, MVOC_ERR_INVALID_ARG, "mvoc_attn_pair_fwd: pair_batches=%d must be positive",
                  pair_batches);
     return attn::run(q, k, v, o, B, H, Nq, Nk, D, st, pair_batches, scale, dtype, variant, stream, "mvoc_attn_pair_fwd");
+}
+
+// Diagnostics: mvoc_attn_fwd (or the pair kernel when pair_batches > 0) with clock64() time stamps of CTA (0,0,0):
+// trace[j*8 + e] for key block j and event e — 0 softmax waits for S, 1 S ready, 2 maximum known, 3 exponentials
+// done, 4 P buffer free, 5 P published (softmax thread 0); 6 Q K^T issued, 7 P V issued (MMA lane).
+extern "C" int mvoc_attn_fwd_trace(const void* q, const void* k, const void* v, void* o, int B, int H, int Nq, int Nk,
+                                   int D, const int64_t* strides12, int pair_batches, float scale, int dtype, int variant,
+                                   long long* trace, void* stream) {
+    MVOC_REQUIRE(strides12 && trace, MVOC_ERR_INVALID_ARG, "mvoc_attn_fwd_trace: null pointer");
+    int64_t st[12];
+    for (int i = 0; i < 12; ++i) st[i] = strides12[i];
+    return attn::run(q, k, v, o, B, H, Nq, Nk, D, st, pair_batches, scale, dtype, variant, stream, "mvoc_attn_fwd_trace",
+                     trace);
 }

@@ -304,6 +304,7 @@ class I2VGenXLPipeline:
         max_steps: Optional[int] = None,
         keep: bool = True,
         save_dtype=torch.float16,
+        on_step: Optional[Callable] = None,
     ) -> Dict[int, torch.Tensor]:
         """DDIM inversion loop, pipeline_i2vgen_xl.py:1914-2003 (guidance 1.0 => batch 1, :517).
         Returns {t: latents at level t}; with output_dir also writes ddim_latents_{t}.pt (:1988-1993)."""
@@ -324,6 +325,8 @@ class I2VGenXLPipeline:
                 saved[t] = x.clone()                                            # :1986
             if output_dir is not None:
                 save_ddim_latents_at_t(x, t, output_dir, save_dtype)            # :1988-1993
+            if on_step is not None:
+                on_step(t, x)
         return saved
 
 

@@ -36,6 +36,7 @@ class Workload:
     fusion_step: Tuple[int, int] = (0, 1)
     obj_random_noise_fusion: bool = False
     seed: int = 6
+    n_videos: int = 1          # inversion workloads: independent source videos (replicas across GPUs)
 
     @property
     def n_branches(self) -> int:
@@ -47,6 +48,9 @@ WORKLOADS: Dict[str, Workload] = {
     "config1": Workload("config1", "reduced", 8, 32, 32, 1),
     # configs[1] / [3]: full UNet, 16 x 64x64 (512x512 px), bg + 2 objects, boat_surf knobs
     "config2": Workload("config2", "full", 16, 64, 64, 2),
+    # configs[2]: group DDIM inversion of 3 source videos (16 x 64x64 latents, 500 steps, cfg 1.0 => batch 1),
+    # one video per GPU (replicas, no collective; configs/group_inversion/group_config.json shape)
+    "config3": Workload("config3", "full", 16, 64, 64, 0, n_videos=3),
     # configs[4]: 32 x 88x160 (704x1280 px), bg + 3 objects
     "config5": Workload("config5", "full", 32, 88, 160, 3),
     # the benchmarked model and latent size with 2 of the 16 frames: full-architecture GPU parity against the
