@@ -498,7 +498,7 @@ def run_inversion(args, wl, par, dev, rank, world, local):
 
     from mvoc_b200 import ops, synthetic
     from mvoc_b200.parallel import FrameParallel
-    from mvoc_b200.pipeline import I2VGenXLPipeline
+    from mvoc_b200.pipeline import Conditioning, I2VGenXLPipeline
     from mvoc_b200.unet3d import build_unet
 
     torch.backends.cudnn.benchmark = True
@@ -509,17 +509,17 @@ def run_inversion(args, wl, par, dev, rank, world, local):
     vids = []
     for v in mine:
         inv = synthetic.make_inversion_inputs(wl, v)
-        vids.append((inv["latents"].to(dev), bf(inv["prompt_embeds"]), bf(inv["image_embeddings"]),
-                     bf(inv["image_latents"]), inv["fps"].to(dev)))
+        pe, ie, il, fps = bf(inv["prompt_embeds"]), bf(inv["image_embeddings"]), bf(inv["image_latents"]), inv["fps"].to(dev)
+        vids.append((inv["latents"].to(dev), pe, ie, il, fps, Conditioning(pe, ie, il, il, fps)))
     K, W = min(args.steps, wl.inversion_steps), max(args.warmup, 0)
 
     def steps(n, host_io=False):
         out = None
-        for lat, pe, ie, il, fps in vids:
+        for lat, pe, ie, il, fps, cond in vids:
             host = torch.empty(lat.shape, dtype=lat.dtype).pin_memory() if host_io else None
             x = host.copy_(lat.cpu()).to(dev, non_blocking=True) if host_io else lat.clone()
-            saved = pipe.invert(x, pe, ie, il, fps, num_inference_steps=wl.inversion_steps, max_steps=n, keep=False,
-                                on_step=(lambda t, z: host.copy_(z, non_blocking=False)) if host_io else None)
+            pipe.invert(x, pe, ie, il, fps, num_inference_steps=wl.inversion_steps, max_steps=n, keep=False, cond=cond,
+                        on_step=(lambda t, z: host.copy_(z, non_blocking=False)) if host_io else None)
             out = x
         return out
 
@@ -588,8 +588,7 @@ def _finish(pipe, par):
         dog = threading.Timer(45.0, lambda: os._exit(0))
         dog.daemon = True
         dog.start()
-    pipe._graphs.clear()
-    pipe._graph_pool = None
+    pipe.drop_graphs()
     gc.collect()
     torch.cuda.synchronize()
     if par.world > 1:

@@ -253,99 +253,92 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             if (!s_ready) ptx::mbar_wait(b_s_full, (uint32_t)j & 1u, 9);
             ptx::tc_fence_after();
             if (threadIdx.x == 0) trace_at(prm, j, 1);   // S ready
-            // Online softmax at 32-column granularity.  The score row leaves TMEM in 32-column pieces; piece c+1
-            // streams out while piece c is reduced (its maximum: 16 FMNMX3) and exponentiated, so neither the TMEM
-            // read latency nor a full-row maximum sits in front of the exponentials.  The running stabiliser m_used
-            // only moves when a piece exceeds it by more than 2^8 (rare after the first pieces of a row): then the
-            // running O, l, this block's partial sums and its already packed pieces are rescaled.  S is released to
-            // the MMA warp (next Q K^T) as soon as the last piece has landed.
+            // One TMEM read of the whole score row (BN fp32 columns -> BN registers); S is free for the next
+            // Q K^T as soon as it sits in registers, long before the exponentials are done.  (Measured on B200:
+            // reading and reducing the row in 32-column pieces, with or without exponentiating each piece at once,
+            // is slower — 2.27 / 2.31 ms against 2.04 ms at the l0 shape: the waits between the pieces serialise what
+            // the scheduler otherwise overlaps across the 64 independent pairs of the row.)
             uint32_t r[BN];
-            uint32_t pk[BN / 2];
-            uint64_t la = ptx::pack2(0.0f, 0.0f), lb = la, lc = la, ld = la;
-            const uint64_t sl2_2 = ptx::pack2(sl2, sl2);
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c)
+                ptx::tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
+            ptx::tmem_wait_ld();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(b_s_free);
+            if (tail) {  // keys past Nk (zero-filled by TMA) must not take part: exp2(-inf) = 0
+#pragma unroll
+                for (int i = 0; i < BN; ++i)
+                    if (i >= valid) r[i] = 0xff800000u;
+            }
+            // row max: eight independent chains of 3-input max (FMNMX3), 8 deep for a 128-column row
+            float mxc[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) mxc[e] = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < BN; i += 16) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    mxc[e] = ptx::max3(mxc[e], __uint_as_float(r[i + 2 * e]), __uint_as_float(r[i + 2 * e + 1]));
+            }
+            const float mx = fmaxf(ptx::max3(mxc[0], mxc[1], mxc[2]), fmaxf(ptx::max3(mxc[3], mxc[4], mxc[5]), fmaxf(mxc[6], mxc[7])));
             bool pv_waited = false;            // the previous P V is known complete (blocking wait done)
             bool pv_ready = (j == 0);          // ... or seen complete by the non-blocking poll
-            constexpr int NC = BN / 32;
-            ptx::tmem_ld32(tS, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-            ptx::tmem_wait_ld();
-#pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                if (c + 1 < NC) ptx::tmem_ld32(tS + (c + 1) * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[(c + 1) * 32]));
-                if (tail) {  // keys past Nk (zero-filled by TMA) must not take part: exp2(-inf) = 0
-#pragma unroll
-                    for (int i = c * 32; i < c * 32 + 32; ++i)
-                        if (i >= valid) r[i] = 0xff800000u;
-                }
-                // maximum of the piece: four independent chains of 3-input max (FMNMX3)
-                float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-                for (int i = c * 32; i < c * 32 + 32; i += 8) {
-                    mx0 = ptx::max3(mx0, __uint_as_float(r[i + 0]), __uint_as_float(r[i + 1]));
-                    mx1 = ptx::max3(mx1, __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-                    mx2 = ptx::max3(mx2, __uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
-                    mx3 = ptx::max3(mx3, __uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
-                }
-                const float m_new = fmaxf(m_used, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
-                const bool need = (m_new - m_used) * sl2 > RESCALE_LOG2_THRESHOLD;   // first piece of a row: inf > 8
+            if (j == 0) {
+                m_used = mx;
+            } else {
+                const float m_new = fmaxf(m_used, mx);
+                const bool need = (m_new - m_used) * sl2 > RESCALE_LOG2_THRESHOLD;
                 if (__any_sync(0xffffffffu, need)) {
-                    const float f = need ? ptx::ex2_approx((m_used - m_new) * sl2) : 1.0f;   // first piece: 2^-inf = 0
+                    // rescale the running O and l (rare after the first blocks)
+                    ptx::mbar_wait(b_pv_done, (uint32_t)(j - 1) & 1u, 10);
+                    ptx::tc_fence_after();
+                    pv_waited = true;
+                    const float f = need ? ptx::ex2_approx((m_used - m_new) * sl2) : 1.0f;
                     if (need) m_used = m_new;
-                    const uint64_t f2 = ptx::pack2(f, f), z2 = ptx::pack2(0.0f, 0.0f);
                     l_sum *= f;
-                    la = ptx::fma2(la, f2, z2), lb = ptx::fma2(lb, f2, z2), lc = ptx::fma2(lc, f2, z2), ld = ptx::fma2(ld, f2, z2);
 #pragma unroll
-                    for (int k = 0; k < c * 16; ++k) pk[k] = Pack2<T>::scale(pk[k], f);
-                    if (j > 0) {   // the running O (rare after the first blocks)
-                        if (!pv_waited) {
-                            ptx::mbar_wait(b_pv_done, (uint32_t)(j - 1) & 1u, 10);
-                            ptx::tc_fence_after();
-                            pv_waited = true;
-                        }
+                    for (int c = 0; c < kNV * HD / 32; ++c) {
+                        uint32_t o[32];
+                        ptx::tmem_ld32(tO + c * 32, o);
+                        ptx::tmem_wait_ld();
 #pragma unroll
-                        for (int oc = 0; oc < kNV * HD / 32; ++oc) {
-                            uint32_t o[32];
-                            ptx::tmem_ld32(tO + oc * 32, o);
-                            ptx::tmem_wait_ld();   // (also completes the score piece in flight)
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-                            ptx::tmem_st32(tO + oc * 32, o);
-                        }
-                        ptx::tmem_wait_st();
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+                        ptx::tmem_st32(tO + c * 32, o);
                     }
-                }
-                // p = exp2(s * scale*log2e - m * scale*log2e) on pairs (FFMA2); the exponential goes to the MUFU or,
-                // for the pairs selected by kEmuMask, to the FMA-pipe polynomial; packed row sums (FADD2).
-                const uint64_t negm_2 = ptx::pack2(-m_used * sl2, -m_used * sl2);
-#pragma unroll
-                for (int k = c * 16; k < c * 16 + 16; ++k) {
-                    const uint64_t x2 = ptx::fma2(ptx::pack2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1])),
-                                                  sl2_2, negm_2);
-                    float p0, p1;
-                    if ((kEmuMask >> (k & 7)) & 1u) {
-                        ptx::ex2_poly2(x2, p0, p1);
-                    } else {
-                        float x0, x1;
-                        ptx::unpack2(x2, x0, x1);
-                        p0 = ptx::ex2_approx(x0);
-                        p1 = ptx::ex2_approx(x1);
-                    }
-                    const uint64_t p2 = ptx::pack2(p0, p1);
-                    if ((k & 3) == 0) la = ptx::add2(la, p2);
-                    else if ((k & 3) == 1) lb = ptx::add2(lb, p2);
-                    else if ((k & 3) == 2) lc = ptx::add2(lc, p2);
-                    else ld = ptx::add2(ld, p2);
-                    pk[k] = Pack2<T>::rn(p0, p1);
-                }
-                // halfway through: poll (without blocking) whether the previous P V has completed, so that the wait
-                // in front of the P store costs nothing when it has (an mbarrier wait costs ~130 clocks even then)
-                if (c == NC / 2 && !pv_waited && !pv_ready) pv_ready = ptx::mbar_test(b_pv_done, (uint32_t)(j - 1) & 1u);
-                if (c + 1 < NC) ptx::tmem_wait_ld();
-                if (c + 2 == NC || NC == 1) {   // every piece has left TMEM
-                    ptx::tc_fence_before();
-                    ptx::mbar_arrive(b_s_free);
+                    ptx::tmem_wait_st();
                 }
             }
-            if (threadIdx.x == 0) trace_at(prm, j, 2);   // (kept for the trace layout: pieces done)
+            if (threadIdx.x == 0) trace_at(prm, j, 2);   // row in registers, maximum known, rescale decided
+            // p = exp2(s * scale*log2e - m * scale*log2e) on pairs (FFMA2); the exponential goes to the MUFU or,
+            // for the pairs selected by kEmuMask, to the FMA-pipe polynomial; packed row sums (FADD2).
+            const uint64_t sl2_2 = ptx::pack2(sl2, sl2);
+            const uint64_t negm_2 = ptx::pack2(-m_used * sl2, -m_used * sl2);
+            uint32_t pk[BN / 2];
+            uint64_t la = ptx::pack2(0.0f, 0.0f), lb = la, lc = la, ld = la;
+#pragma unroll
+            for (int k = 0; k < BN / 2; ++k) {
+                const uint64_t x2 = ptx::fma2(ptx::pack2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1])),
+                                              sl2_2, negm_2);
+                float p0, p1;
+                if ((kEmuMask >> (k & 7)) & 1u) {
+                    ptx::ex2_poly2(x2, p0, p1);
+                } else {
+                    float x0, x1;
+                    ptx::unpack2(x2, x0, x1);
+                    p0 = ptx::ex2_approx(x0);
+                    p1 = ptx::ex2_approx(x1);
+                }
+                const uint64_t p2 = ptx::pack2(p0, p1);
+                if ((k & 3) == 0) la = ptx::add2(la, p2);
+                else if ((k & 3) == 1) lb = ptx::add2(lb, p2);
+                else if ((k & 3) == 2) lc = ptx::add2(lc, p2);
+                else ld = ptx::add2(ld, p2);
+                pk[k] = Pack2<T>::rn(p0, p1);
+                // two thirds through: poll (without blocking) whether the previous P V has completed, so that the wait
+                // in front of the P store costs nothing when it has (an mbarrier wait costs ~130 clocks even then)
+                if (k == (BN / 2) * 2 / 3 && !pv_waited && !pv_ready)
+                    pv_ready = ptx::mbar_test(b_pv_done, (uint32_t)(j - 1) & 1u);
+            }
             {
                 float s0, s1;
                 ptx::unpack2(ptx::add2(ptx::add2(la, lb), ptx::add2(lc, ld)), s0, s1);

@@ -651,8 +651,7 @@ static int launch_cfg(const Problem& pb, Params prm, int b1, int b2, int b3, cud
 }
 
 template <int BN, int kEpi>
-static int launch_bn(const Problem& pb, const Params& prm, int b1, int b2, int b3, cudaStream_t s) {
-    const bool two = (pb.variant & 1) != 0;
+static int launch_bn(const Problem& pb, const Params& prm, int b1, int b2, int b3, cudaStream_t s, bool two) {
     if (pb.dtype == MVOC_F16) {
         if (two) return launch_cfg<Cfg<BN, true, kEpi>, __half>(pb, prm, b1, b2, b3, s);
         return launch_cfg<Cfg<BN, false, kEpi>, __half>(pb, prm, b1, b2, b3, s);
@@ -697,23 +696,47 @@ static int run(const Problem& pb, cudaStream_t stream) {
     prm.has_res = pb.residual != nullptr;
     prm.gate_off = (int)pb.N;
     prm.dbg = (pb.variant >> 20) & 3;
-    int BN = (pb.variant >> 8) & 0x1ff;
-    if (pb.geglu) {
-        if (BN == 0) BN = pb.N % 128 == 0 ? 256 : 128;
-        MVOC_REQUIRE((BN == 256 || BN == 128) && pb.N % (BN / 2) == 0, MVOC_ERR_UNSUPPORTED,
-                     "%s: GEGLU tile %d does not divide F=%lld", what, BN, (long long)pb.N);
-        if (BN == 256) return launch_bn<256, EPI_GEGLU>(pb, prm, b1, b2, b3, stream);
-        return launch_bn<128, EPI_GEGLU>(pb, prm, b1, b2, b3, stream);
+    // Tile width and CTA mode.  Measured on B200 (profiles/r02_gemm_check_time_*.txt): a K chunk of 64 costs about
+    // 256 + 2 BN clocks on one CTA and 160 + 2 BN on a CTA pair (two 128-row tiles), so wide tiles win — until the
+    // problem has fewer tiles than the chip has SMs (the low-resolution levels, and every level once the frames are
+    // sharded over 8 GPUs), where narrower tiles and single CTAs fill more SMs.  Pick the cheapest of
+    // waves x chunk cost; variant bit 0 allows CTA pairs, bits 8.. force a width.
+    const int forced = (pb.variant >> 8) & 0x1ff;
+    const bool allow_pair = (pb.variant & 1) != 0;
+    const int64_t m_tiles = (int64_t)prm.t1 * prm.t2 * ((pb.d3 + b3 - 1) / b3);
+    const int sms = num_sms();
+    const int widths_lin[5] = {256, 192, 160, 128, 64};
+    const int widths_geglu[2] = {256, 128};
+    const int* widths = pb.geglu ? widths_geglu : widths_lin;
+    const int n_widths = pb.geglu ? 2 : 5;
+    int BN = 0;
+    bool two = false;
+    double best = 0.0;
+    for (int i = 0; i < n_widths; ++i) {
+        const int w = widths[i];
+        const int out_cols = pb.geglu ? w / 2 : w;
+        if (pb.N % out_cols != 0 || (forced && forced != w)) continue;
+        const int64_t n_tiles = pb.N / out_cols;
+        for (int pair = allow_pair ? 1 : 0; pair >= 0; --pair) {
+            const int64_t units = pair ? ((m_tiles + 1) / 2) * n_tiles : m_tiles * n_tiles;
+            const int64_t slots = pair ? sms / 2 : sms;
+            const double waves = (double)((units + slots - 1) / slots);
+            const double cost = waves * ((pair ? 160.0 : 256.0) + 2.0 * w);
+            if (BN == 0 || cost < best * 0.999) best = cost, BN = w, two = pair != 0;
+        }
     }
-    if (BN == 0) BN = pb.N % 256 == 0 ? 256 : pb.N % 192 == 0 ? 192 : pb.N % 160 == 0 ? 160 : pb.N % 128 == 0 ? 128 : 64;
-    MVOC_REQUIRE(pb.N % BN == 0, MVOC_ERR_UNSUPPORTED, "%s: tile width %d does not divide N=%lld", what, BN,
+    MVOC_REQUIRE(BN != 0, MVOC_ERR_UNSUPPORTED, "%s: no tile width (forced %d) divides N=%lld", what, forced,
                  (long long)pb.N);
+    if (pb.geglu) {
+        if (BN == 256) return launch_bn<256, EPI_GEGLU>(pb, prm, b1, b2, b3, stream, two);
+        return launch_bn<128, EPI_GEGLU>(pb, prm, b1, b2, b3, stream, two);
+    }
     switch (BN) {
-        case 256: return launch_bn<256, EPI_LINEAR>(pb, prm, b1, b2, b3, stream);
-        case 192: return launch_bn<192, EPI_LINEAR>(pb, prm, b1, b2, b3, stream);
-        case 160: return launch_bn<160, EPI_LINEAR>(pb, prm, b1, b2, b3, stream);
-        case 128: return launch_bn<128, EPI_LINEAR>(pb, prm, b1, b2, b3, stream);
-        case 64: return launch_bn<64, EPI_LINEAR>(pb, prm, b1, b2, b3, stream);
+        case 256: return launch_bn<256, EPI_LINEAR>(pb, prm, b1, b2, b3, stream, two);
+        case 192: return launch_bn<192, EPI_LINEAR>(pb, prm, b1, b2, b3, stream, two);
+        case 160: return launch_bn<160, EPI_LINEAR>(pb, prm, b1, b2, b3, stream, two);
+        case 128: return launch_bn<128, EPI_LINEAR>(pb, prm, b1, b2, b3, stream, two);
+        case 64: return launch_bn<64, EPI_LINEAR>(pb, prm, b1, b2, b3, stream, two);
         default: break;
     }
     set_error("%s: unsupported tile width %d (256, 192, 160, 128, 64)", what, BN);

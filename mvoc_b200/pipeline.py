@@ -114,7 +114,14 @@ class I2VGenXLPipeline:
         self._t_dev = None
         self._static_in = {}
         self.scheduler: Optional[DDIMSchedule] = None
-        self._cond_cache = None
+        self._cond_caches = {}     # id(cond) -> {"key": cond (strong ref), "ctx", "il", "fps_emb"}; a few conditionings
+
+
+    def drop_graphs(self) -> None:
+        """Forget every captured graph.  The private pool goes with them: torch asserts when a capture re-uses a
+        pool handle whose graphs have all been destroyed."""
+        self._graphs.clear()
+        self._graph_pool = None
 
     def static_input(self, shape, device) -> torch.Tensor:
         """Persistent UNet input buffer [n_branches, 4, T, h, w] (captured graphs read from it)."""
@@ -148,7 +155,7 @@ class I2VGenXLPipeline:
         b, c, T, h, w = sample.shape
         f0, f1 = par.frame_range(T) if par.world > 1 else (0, T)
         tl = f1 - f0
-        cache = self._cond_cache
+        cache = self._cond_caches.get(id(cond))
         if cache is None or cache["key"] is not cond:
             ctx = unet.context(cond.prompt_embeds, cond.image_latents, cond.image_embeddings)
             ctx = ctx.repeat_interleave(tl, dim=0)                              # one context per frame (:255-260)
@@ -156,8 +163,10 @@ class I2VGenXLPipeline:
             il = il.view(b, T, c, h, w)[:, f0:f1].reshape(b * tl, c, h, w).contiguous()
             fps_emb = unet.fps_embedding(unet.time_proj(cond.fps).to(unet.dtype))
             cache = {"key": cond, "ctx": ctx, "il": il, "fps_emb": fps_emb}
-            self._cond_cache = cache
-            self._graphs.clear()         # captured graphs point at the previous conditioning tensors
+            if len(self._cond_caches) >= 8:      # graphs captured for an evicted conditioning point at freed tensors
+                self._cond_caches.clear()
+                self.drop_graphs()
+            self._cond_caches[id(cond)] = cache
         if self._t_dev is None:
             self._t_dev = torch.zeros(1, dtype=torch.int64, device=sample.device)
         self._t_dev.fill_(int(t))        # device-side timestep: the captured graph reads it at replay time
@@ -305,13 +314,15 @@ class I2VGenXLPipeline:
         keep: bool = True,
         save_dtype=torch.float16,
         on_step: Optional[Callable] = None,
+        cond: Optional[Conditioning] = None,
     ) -> Dict[int, torch.Tensor]:
         """DDIM inversion loop, pipeline_i2vgen_xl.py:1914-2003 (guidance 1.0 => batch 1, :517).
         Returns {t: latents at level t}; with output_dir also writes ddim_latents_{t}.pt (:1988-1993)."""
         if guidance_scale > 1.0:
             raise NotImplementedError("inversion with classifier-free guidance is not used by the reference configs")
         sched = DDIMSchedule(num_inference_steps, inverse=True)
-        cond = Conditioning(prompt_embeds, image_embeddings, image_latents, image_latents, fps)
+        if cond is None:    # callers that invert the same video repeatedly pass the object: graphs are keyed on it
+            cond = Conditioning(prompt_embeds, image_embeddings, image_latents, image_latents, fps)
         saved: Dict[int, torch.Tensor] = {}
         x = latents
         for i, t in enumerate(sched.timesteps):
@@ -344,7 +355,7 @@ def init_pnp(pipe: I2VGenXLPipeline, scheduler: DDIMSchedule, config) -> dict:
     spa_ts = ts[:spa_t] if spa_t >= 0 else []
     tmp_ts = ts[:tmp_t] if tmp_t >= 0 else []
     pnp_utils._MASKS.clear()       # a new run: drop the token masks (and graphs keyed on them) of the previous one
-    pipe._graphs.clear()
+    pipe.drop_graphs()
     pnp_utils.modify_diffuser_attention_forward(pipe.unet)
     pnp_utils.register_temp_attention_pnp(pipe, tmp_ts, config.inject_background)
     pnp_utils.register_spatial_attention_pnp(pipe, spa_ts, config.inject_background)

@@ -31,7 +31,7 @@ def main():
         _cabi.check(rc, "mvoc_attn_fwd_trace")
     torch.cuda.synchronize()
     t = trace.view(nblk, 8).cpu()
-    names = ["wait S", "pieces (load, max, exp)", "row sum", "wait PV", "store P"]
+    names = ["wait S", "load+max", "exp loop", "wait PV", "store P"]
     print(f"B={B} H={H} N={N} pair={pair}: clocks of CTA (0,0,0), softmax thread 0, per key block ({bn} keys)")
     tot = [0.0] * 6
     cnt = 0

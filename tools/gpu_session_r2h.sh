@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # Round-2 session H: piece-wise online softmax (attention), trace + timings + full suite + bench + config3 bench.
 set -u
-TAG="r02h"
+TAG="r02i"
 OUT=gpurun_out
 mkdir -p "$OUT"
 run() {
