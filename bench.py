@@ -261,8 +261,13 @@ def run_mvoc(args):
 
     lib = _cabi.load()
     _cabi.check(lib.mvoc_device_check(local), "mvoc_device_check")
-    if synthetic.WORKLOADS[args.workload].n_obj == 0:
+    wl0 = synthetic.WORKLOADS[args.workload]
+    if wl0.n_obj == 0:
         os.environ["MVOC_EXCHANGE"] = "nccl"      # replicas exchange nothing: no peer arena
+    elif world > 1 and "MVOC_EXCHANGE_ARENA_MB" not in os.environ:
+        # every temporal operator of a forward bump-allocates two buffers of (tensor / P) bytes: ~60 l0-sized ones
+        l0 = wl0.n_branches * wl0.n_frames * wl0.latent_h * wl0.latent_w * 320 * 2
+        os.environ["MVOC_EXCHANGE_ARENA_MB"] = str(int(min(32768, max(4096, 60 * l0 / world / 2 ** 20))))
     par = FrameParallel.from_env(dev)  # world_size 1 => no-op
 
     wl = synthetic.WORKLOADS[args.workload]
@@ -537,13 +542,18 @@ def run_inversion(args, wl, par, dev, rank, world, local):
     if rank == 0:
         clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = ops.launch_count
     ev0.record()
     steps(K)
     ev1.record()
     barrier()
-    launches = ops.launch_count - l0
     clk = clocks.stop() if rank == 0 else None
+    # launches of this library per timed region: counted on ONE eager step per video (graph replays do not pass
+    # through the Python wrappers), times the K steps
+    graphs_on, pipe.use_cuda_graphs = pipe.use_cuda_graphs, False
+    l0 = ops.launch_count
+    steps(1)
+    launches = (ops.launch_count - l0) * K
+    pipe.use_cuda_graphs = graphs_on
     ms_step = par_all.max_over_ranks(ev0.elapsed_time(ev1)) / K
     barrier()
     t0 = time.perf_counter()
