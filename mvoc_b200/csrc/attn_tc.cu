@@ -134,8 +134,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         ptx::prefetch_tensormap(&tm_v);
         ptx::mbar_init(b_q_full, 1);
         ptx::mbar_init(b_s_full, 1);
-        ptx::mbar_init(b_s_free, 128);
-        ptx::mbar_init(b_p_full, 128);
+        ptx::mbar_init(b_s_free, 4);     // one arrival per softmax warp (an elected lane after __syncwarp): 128
+        ptx::mbar_init(b_p_full, 4);     // per-thread arrivals serialise on the barrier word in front of the MMA warp
         ptx::mbar_init(b_pv_done, 1);
         for (int s = 0; s < kStages; ++s) {
             ptx::mbar_init(b_k_full + 8 * s, 1);
@@ -264,7 +264,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 ptx::tmem_ld32(tS + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&r[c * 32]));
             ptx::tmem_wait_ld();
             ptx::tc_fence_before();
-            ptx::mbar_arrive(b_s_free);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(b_s_free);
             if (tail) {  // keys past Nk (zero-filled by TMA) must not take part: exp2(-inf) = 0
 #pragma unroll
                 for (int i = 0; i < BN; ++i)
@@ -358,7 +359,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             s_ready = (j + 1 < n_blocks) && ptx::mbar_test(b_s_full, (uint32_t)(j + 1) & 1u);
             ptx::tmem_wait_st();
             ptx::tc_fence_before();
-            ptx::mbar_arrive(b_p_full);
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(b_p_full);
             if (threadIdx.x == 0) trace_at(prm, j, 5);   // P published
         }
         // ---- epilogue: O / l -> 16-bit -> global --------------------------------
