@@ -458,6 +458,14 @@ def run_mvoc(args):
         "exchange_calls_per_step": (sum(summ[k][0] for k in ex_keys) / K) if ex_keys else None,
     }
 
+    # where the (eager-replayed) step goes: the twelve heaviest timer keys, work in TFLOP/s or GB/s by kernel family
+    tops = sorted(summ.items(), key=lambda kv: -kv[1][1])[:12]
+    extra["top"] = [{"key": "/".join(str(x) for x in k), "calls_per_step": n / K, "ms_per_step": ms / K,
+                     "rate": (w / (ms / 1e3) / (1e12 if k[0] in ("gemm", "attn", "attn_inject", "attn_pair") else 1e9))
+                     if ms else None,
+                     "rate_unit": "TFLOP/s" if k[0] in ("gemm", "attn", "attn_inject", "attn_pair") else "GB/s"}
+                    for k, (n, ms, w) in tops]
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ---------------------------------------------
     cpu = None
     if args.gpus == 1 and not args.no_cpu_baseline:
