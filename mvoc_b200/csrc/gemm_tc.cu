@@ -16,12 +16,13 @@
 // buffer, no halo copy.  A second (A, W) source appended to the K loop fuses the resnet's 1x1 shortcut conv
 // into conv2's accumulator.
 //
-// CTA (192 threads, one per SM, persistent over tiles, static round-robin schedule):
+// CTA (320 threads, one per SM, persistent over tiles, static round-robin schedule):
 //   warp 0     TMA producer: ring of kStages {A 128x64, W BNx64} 128-byte-swizzled stages
 //   warp 1     MMA issuer (one lane): tcgen05.mma 128 x BN x 16 into one of TWO accumulator buffers in TMEM,
 //              so the epilogue of tile i overlaps the main loop of tile i+1; owns the TMEM allocation
-//   warps 2-5  epilogue: thread = TMEM lane = output row; 32-column slabs: tcgen05.ld -> + bias -> (+ residual,
-//              TMA-loaded into the staging buffer one slab ahead) -> (GEGLU) -> bf16 -> swizzled smem -> TMA store
+//   warps 2-9  epilogue, two warps per TMEM lane quarter taking alternate 32-column slabs: thread = TMEM lane =
+//              output row; tcgen05.ld -> + bias -> (+ residual, TMA-loaded into the staging buffer two slabs ahead)
+//              -> (GEGLU) -> bf16 -> swizzled smem -> TMA store of the warp's 32-row box
 // kTwoCta: the same kernel as a CTA PAIR (cluster of 2, tcgen05 cta_group::2): one 256 x BN tile per pair, each
 // CTA stages its own 128 rows of A and HALF of the weight tile, the leader issues M = 256 MMAs that read both
 // halves — weight traffic from L2 per CTA halves.
@@ -33,11 +34,24 @@
 namespace mvoc {
 namespace gemm {
 
+// Relative cost of one 64-element K chunk of a tile by tile width, measured on B200 with ONE convolution whose Cout
+// every width divides (profiles/r02_gemm_width_*.txt: time per tile-chunk = width / TFLOP/s).  The striking fact:
+// it is nearly independent of the width — a tcgen05.mma with both operands in shared memory takes ~128 clocks per
+// 128-row K = 16 step whatever N <= 256 is (the A-operand read paces it), so a tile's efficiency is N / 256 and the
+// number of column tiles is what matters.  256-wide single-CTA tiles pay extra for the shared-memory fill.
+static double chunk_cost(int w, bool pair) {
+    switch (w) {
+        case 256: return pair ? 152.0 : 191.0;
+        case 192: return pair ? 133.0 : 146.0;
+        case 160: return pair ? 143.0 : 146.0;
+        case 128: return pair ? 136.0 : 138.0;
+        default: return pair ? 119.0 : 121.0;   // 64
+    }
+}
+
 constexpr int BM = 128;                    // rows (pixels) per CTA tile
 constexpr int KC = 64;                     // K elements per stage = one 128-byte swizzled row
 constexpr int A_BYTES = BM * KC * 2;       // 16 KB
-constexpr int N_OUT = 3;                   // staging buffers per epilogue warp (residual prefetched two slabs ahead)
-constexpr int THREADS = 192;
 constexpr int SMEM_LIMIT = 232448;         // 227 KB per CTA
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int MAX_TAPS = 9;
@@ -53,18 +67,30 @@ struct Cfg {
     static constexpr int B_BYTES = B_ROWS * KC * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int OUT_COLS = kEpi == EPI_GEGLU ? BN / 2 : BN;   // output columns of a tile
-    // epilogue slab: 64 columns (128-byte rows, 128B swizzle) when the tile divides into them, else 32 (64B swizzle);
-    // the GEGLU epilogue holds value AND gate columns in registers, so it stays at 32
-    static constexpr int SLAB = (kEpi == EPI_LINEAR && OUT_COLS % 64 == 0) ? 64 : 32;
+    // Epilogue: 32-column slabs (64-byte staging rows, 64B swizzle) on EIGHT warps, two per TMEM lane quarter taking
+    // alternate slabs.  With four warps each one sat alone on its scheduler and issued one instruction per ~6.6
+    // clocks (ncu, profiles/r02_ncu_linear_summary.txt): a 192-column tile cost ~7000 clocks of epilogue against
+    // 2560 clocks of MMAs at K = 320, which is what bounded every short-K Linear.
+    static constexpr int SLAB = 32;
     static constexpr int SLABS = OUT_COLS / SLAB;
-    static constexpr int WSLAB_BYTES = 32 * SLAB * 2;        // one warp's 32 rows of one slab: 2 or 4 KB
+    static constexpr int WSLAB_BYTES = 32 * SLAB * 2;        // one warp's 32 rows of one slab: 2 KB
+    static constexpr int EPI_WARPS = 8;
+    static constexpr int HALVES = EPI_WARPS / 4;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    // Staging buffers per epilogue warp = RES_AHEAD + ST_PENDING: while slab g is processed the residual of slab
+    // g + RES_AHEAD is being TMA-loaded and up to ST_PENDING TMA stores may still be reading their buffers (lanes
+    // other than lane 0 run one slab ahead of its wait, hence ST_PENDING <= N_OUT - 2).  Deeper variants (3 ahead,
+    // 3 pending) were measured and only cost pipeline stages (profiles/r02_gemm_epilogue_experiments.txt).
+    static constexpr int RES_AHEAD = 2;
+    static constexpr int ST_PENDING = 1;
+    static constexpr int N_OUT = RES_AHEAD + ST_PENDING;
     static constexpr int out_off = 0;                        // staging first: 1024-byte aligned like the stages
-    static constexpr int stage_off = 4 * N_OUT * WSLAB_BYTES;
+    static constexpr int stage_off = EPI_WARPS * N_OUT * WSLAB_BYTES;
     static constexpr int kStagesFit = (SMEM_LIMIT - stage_off - 512) / STAGE_BYTES;
     static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr int bar_off = stage_off + kStages * STAGE_BYTES;
-    // barriers: full[kStages], empty[kStages], acc_full[2], acc_empty[2], res_full[4 warps][N_OUT]
-    static constexpr int n_bars = 2 * kStages + 4 + 4 * N_OUT;
+    // barriers: full[kStages], empty[kStages], acc_full[2], acc_empty[2], res_full[EPI_WARPS][N_OUT]
+    static constexpr int n_bars = 2 * kStages + 4 + EPI_WARPS * N_OUT;
     static constexpr int tmem_ptr_off = bar_off + n_bars * 8;
     static constexpr int alloc = tmem_ptr_off + 16;
     static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "BN: multiple of 32 in [64, 256]");
@@ -84,10 +110,13 @@ struct Params {
     int k_chunks[2];           // K / 64 per source
     int taps[2];
     int8_t off[2][MAX_TAPS][3];   // coordinate shift of (d1, d2, d3) per tap
+    int tail_cols;             // > 0: the LAST column tile is only this wide (multiple of 64; N % BN); its MMAs run at
+                               // N = tail_cols and the epilogue skips the slabs beyond it
     int gate_off;              // GEGLU: row of W where the gate half starts (F)
     int has_res;
     int dbg;                   // timing experiments only (results are garbage): 1 = never reload the weight stage,
-                               // 2 = never reload the activation stage (variant bits 20, 21)
+                               // 2 = never reload the activation stage, 4 = no TMA stores, 8 = no epilogue work at
+                               // all (accumulators released at once)  (variant bits 20..23)
     const void* bias;          // [N] (GEGLU: [2F]) in the activation dtype, or nullptr
 };
 
@@ -190,6 +219,24 @@ __device__ __forceinline__ Vec16 ldg16_nc(const void* p) {
     return v;
 }
 
+// f[0..7] += the eight 16-bit values of v.  bf16 -> fp32 is a shift (low half) or a mask (high half): two integer
+// instructions per pair instead of the three the generic element-wise conversion compiles to.
+template <typename T>
+__device__ __forceinline__ void add8(float (&f)[8], const Vec16& v) {
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            f[2 * i] += __uint_as_float(v.w[i] << 16);
+            f[2 * i + 1] += __uint_as_float(v.w[i] & 0xffff0000u);
+        }
+    } else {
+        float t[8];
+        unpack8<T>(v, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] += t[i];
+    }
+}
+
 // x -> 0.5 x (1 + erf(x / sqrt 2)): exact GELU (torch.nn.functional.gelu default).  erf by Abramowitz-Stegun 7.1.26
 // (|error| <= 1.5e-7, far below the 16-bit rounding of the product): one reciprocal, one exp2, a degree-5 Horner.
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -231,12 +278,20 @@ __device__ __forceinline__ TileCoord decode_tile(const Params& p, int t, uint32_
     return tc;
 }
 
+// accumulator columns in use for column tile n_tile
+template <typename C>
+__device__ __forceinline__ int tile_cols(const Params& p, int n_tile) {
+    if (C::kEpi == EPI_LINEAR && p.tail_cols > 0 && n_tile == p.n_tiles - 1) return p.tail_cols;
+    return C::BN;
+}
+
 template <typename C, typename T>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(C::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_w0,
                const __grid_constant__ CUtensorMap tm_a1, const __grid_constant__ CUtensorMap tm_w1,
                const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
-               const Params prm) {
+               const __grid_constant__ Params prm) {   // __grid_constant__: the dynamically indexed tap table is read
+                                                       // from the constant bank instead of a per-thread local copy
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t sbase = smem_u32(smem_raw);
     if ((sbase & 1023u) != 0u) {
@@ -244,6 +299,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         __trap();
     }
     constexpr int kStages = C::kStages;
+    constexpr int N_OUT = C::N_OUT;
     const uint32_t sOut = sbase + C::out_off;
     const uint32_t sStage = sbase + C::stage_off;
     const uint32_t bars = sbase + C::bar_off;
@@ -272,9 +328,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         }
         for (int b = 0; b < 2; ++b) {
             ptx::mbar_init(b_acc_full + 8 * b, 1);
-            ptx::mbar_init(b_acc_empty + 8 * b, C::kTwoCta ? 8 : 4);   // one arrive per epilogue warp (of both CTAs)
+            ptx::mbar_init(b_acc_empty + 8 * b, (C::kTwoCta ? 2 : 1) * C::EPI_WARPS);   // one arrive per epilogue warp (of both CTAs)
         }
-        for (int b = 0; b < 4 * N_OUT; ++b) ptx::mbar_init(b_res + 8 * b, 1);
+        for (int b = 0; b < C::EPI_WARPS * N_OUT; ++b) ptx::mbar_init(b_res + 8 * b, 1);
         ptx::fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_t<C::kTwoCta>(s_tmem_ptr, TMEM_COLS);
@@ -322,7 +378,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                                                          tc.n_tile * NP + prm.gate_off, tap, 0);
                                 }
                             } else {
-                                const int wrow = tc.n_tile * C::BN + (C::kTwoCta ? (int)crank * C::B_ROWS : 0);
+                                // pair mode: this CTA stages its half of the tile's weight rows (a narrower tail tile
+                                // still loads a full box: the rows beyond the tail are never read by its MMAs)
+                                const int wrow = tc.n_tile * C::BN +
+                                                 (C::kTwoCta ? (int)crank * (tile_cols<C>(prm, tc.n_tile) / 2) : 0);
                                 tma_load_tile<C::kTwoCta>(sB, mw, full, kc * KC, wrow, tap, 0);
                             }
                         }
@@ -333,9 +392,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
         // ===================== MMA issuer (pair mode: the leader CTA only) =====================
         if (lane == 0 && leader) {
             constexpr bool kF16 = sizeof(T) == 2 && !std::is_same<T, __nv_bfloat16>::value;
-            constexpr uint32_t IDESC = idesc_16(C::kTwoCta ? 256 : 128, C::BN, kF16);
             uint32_t it = 0, lt = 0;
             for (int t = first_tile; t < prm.total_tiles; t += tile_stride, ++lt) {
+                const uint32_t IDESC = idesc_16(C::kTwoCta ? 256 : 128, tile_cols<C>(prm, t % prm.n_tiles), kF16);
                 const uint32_t buf = lt & 1u;
                 ptx::mbar_wait(b_acc_empty + 8 * buf, ((lt >> 1) & 1u) ^ 1u, 2);
                 ptx::tc_fence_after();
@@ -360,29 +419,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
             }
         }
     } else {
-        // ===================== epilogue (warps 2-5), one independent pipeline per warp =====================
+        // ===================== epilogue (warps 2-9), one independent pipeline per warp =====================
         // Warp q owns rows [32q, 32q+32) of the tile (the TMEM lanes it may read).  Per slab of SLAB columns:
         // tcgen05.ld (issued one slab ahead) -> + bias -> (+ residual, TMA-loaded into the staging buffer two slabs
         // ahead) -> (GEGLU) -> 16-bit -> swizzled staging -> TMA store of the warp's own 32-row box.  No barrier
         // wider than the warp: lane 0 owns the warp's bulk-async groups and residual barriers.
         constexpr int SLAB = C::SLAB, SLABS = C::SLABS;
         constexpr int CHUNKS = SLAB / 8;                    // 16-byte chunks per staged row
-        const int q = warp & 3;
-        const uint32_t sWarp = sOut + (uint32_t)q * (N_OUT * C::WSLAB_BYTES);
+        constexpr int HALVES = C::HALVES;
+        const int q = warp & 3;              // TMEM lane quarter this warp may read (hardware: warp id % 4)
+        const int ew = warp - 2;             // epilogue warp index
+        const int half = ew >> 2;            // which of the HALVES interleaved slab sequences this warp takes
+        const int my_slabs = (SLABS - half + HALVES - 1) / HALVES;   // slabs half, half + HALVES, ... of every tile
+        const uint32_t sWarp = sOut + (uint32_t)ew * (N_OUT * C::WSLAB_BYTES);
         const uint32_t row_off = (uint32_t)lane * (SLAB * 2);
         // swizzle of the staging rows (what the TMA store expects): 128B -> chunk ^ (row & 7); 64B -> chunk ^ ((row >> 1) & 3)
         const uint32_t sw = SLAB == 64 ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
-        const uint32_t b_res_w = b_res + 8 * (q * N_OUT);
+        const uint32_t b_res_w = b_res + 8 * (ew * N_OUT);
         const T* bias = reinterpret_cast<const T*>(prm.bias);
         // rows 32q.. of the tile inside the (b1, b2, b3) row box
         const int r0 = q * 32;
         const int w1 = r0 % prm.b1, w2 = (r0 / prm.b1) % prm.b2, w3 = r0 / (prm.b1 * prm.b2);
 
-        auto slab_at = [&](uint32_t g, int& col, TileCoord& tc) -> bool {   // slab g of this CTA -> column, row coords
-            const int t = first_tile + (int)(g / SLABS) * tile_stride;
+        auto slab_at = [&](uint32_t g, int& col, TileCoord& tc) -> bool {   // slab g of this warp -> column, row coords
+            const int t = first_tile + (int)(g / my_slabs) * tile_stride;
             if (t >= prm.total_tiles) return false;
             tc = decode_tile<C>(prm, t, crank);
-            col = tc.n_tile * C::OUT_COLS + (int)(g % SLABS) * SLAB;
+            col = tc.n_tile * C::OUT_COLS + ((int)(g % my_slabs) * HALVES + half) * SLAB;
             return true;
         };
         auto prefetch_res = [&](uint32_t g) {   // lane 0 only
@@ -394,10 +457,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
             ptx::tma_load_4d(sWarp + ob * C::WSLAB_BYTES, &tm_res, b_res_w + 8 * ob, col, tc.c1 + w1, tc.c2 + w2,
                              tc.c3 + w3);
         };
-        if (lane == 0 && prm.has_res) {
-            prefetch_res(0);
-            prefetch_res(1);
-        }
+        if (lane == 0 && prm.has_res)
+            for (int a = 0; a < C::RES_AHEAD; ++a) prefetch_res(a);
         uint32_t g = 0, lt = 0;
         for (int t = first_tile; t < prm.total_tiles; t += tile_stride, ++lt) {
             const TileCoord tc = decode_tile<C>(prm, t, crank);
@@ -406,6 +467,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
             ptx::tc_fence_after();
             const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + buf * C::BN;
             const int col0 = tc.n_tile * C::OUT_COLS;
+            if ((prm.dbg & 8) && !prm.has_res) {   // experiment: how fast is the kernel without its epilogue
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (C::kTwoCta) mbar_arrive_leader(b_acc_empty + 8 * buf);
+                    else ptx::mbar_arrive(b_acc_empty + 8 * buf);
+                }
+                continue;
+            }
             uint32_t r[2][SLAB];                               // value columns, two slabs in flight
             uint32_t gt[C::kEpi == EPI_GEGLU ? SLAB : 1];      // gate columns (GEGLU)
             auto issue_ld = [&](int sl, int which) {
@@ -432,41 +502,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                     float f[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(acc[c * 8 + e]);
-                    if (bias) {
-                        float bv[8];
-                        unpack8<T>(ldg16_nc(bias + col0 + sl * SLAB + c * 8), bv);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] += bv[e];
-                    }
+                    if (bias) add8<T>(f, ldg16_nc(bias + col0 + sl * SLAB + c * 8));
                     if constexpr (C::kEpi == EPI_GEGLU) {
                         float gv[8];
 #pragma unroll
                         for (int e = 0; e < 8; ++e) gv[e] = __uint_as_float(gt[c * 8 + e]);
-                        if (bias) {
-                            float bg[8];
-                            unpack8<T>(ldg16_nc(bias + prm.gate_off + col0 + sl * SLAB + c * 8), bg);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) gv[e] += bg[e];
-                        }
+                        if (bias) add8<T>(gv, ldg16_nc(bias + prm.gate_off + col0 + sl * SLAB + c * 8));
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[e] *= gelu_erf(gv[e]);
                     }
                     const uint32_t addr = sbuf + (((uint32_t)c ^ sw) << 4);
-                    if (prm.has_res) {
-                        float rv[8];
-                        unpack8<T>(lds16(addr), rv);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] += rv[e];
-                    }
+                    if (prm.has_res) add8<T>(f, lds16(addr));
                     sts16(addr, pack8<T>(f));
                 }
                 ptx::fence_proxy_async_smem();          // generic-proxy writes -> visible to the TMA store
                 __syncwarp();
                 if (lane == 0) {
-                    tma_store_4d(&tm_out, sWarp + ob * C::WSLAB_BYTES, col0 + sl * SLAB, tc.c1 + w1, tc.c2 + w2, tc.c3 + w3);
+                    if (!(prm.dbg & 4))
+                        tma_store_4d(&tm_out, sWarp + ob * C::WSLAB_BYTES, col0 + sl * SLAB, tc.c1 + w1, tc.c2 + w2, tc.c3 + w3);
                     ptx::bulk_commit();
-                    bulk_wait_read<1>();                 // stores up to slab g-1 have released their buffers
-                    if (prm.has_res) prefetch_res(g + 2);   // into the buffer slab g-1 used
+                    bulk_wait_read<C::ST_PENDING>();     // stores up to slab g - ST_PENDING have released their buffers
+                    if (prm.has_res) prefetch_res(g + C::RES_AHEAD);   // into the buffer slab g - ST_PENDING used
                 }
                 ++g;
             };
@@ -474,20 +530,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                 // the gate makes this epilogue compute-heavy (one erf per output): keep the code small (no unrolling
                 // across slabs: the unrolled form overflowed the instruction cache and ran 1.7x slower on B200)
 #pragma unroll 1
-                for (int sl = 0; sl < SLABS; ++sl) {
+                for (int i = 0; i < my_slabs; ++i) {
+                    const int sl = i * HALVES + half;
                     issue_ld(sl, 0);
                     ptx::tmem_wait_ld();
-                    if (sl + 1 == SLABS) release_acc();
+                    if (i + 1 == my_slabs) release_acc();
                     process(sl, r[0]);
                 }
             } else {
-                issue_ld(0, 0);
+                const int width = tile_cols<C>(prm, tc.n_tile);   // < BN for the tail tile only
+                constexpr int MAX_W = (SLABS + HALVES - 1) / HALVES;
+                if (half * SLAB < width) issue_ld(half, 0);
 #pragma unroll
-                for (int sl = 0; sl < SLABS; ++sl) {
-                    ptx::tmem_wait_ld();                     // slab sl is in r[sl & 1]
-                    if (sl + 1 < SLABS) issue_ld(sl + 1, (sl & 1) ^ 1);   // next slab streams in meanwhile
-                    else release_acc();
-                    process(sl, r[sl & 1]);
+                for (int i = 0; i < MAX_W; ++i) {
+                    if (i < my_slabs) {                          // warp-uniform
+                        const int sl = i * HALVES + half;
+                        ptx::tmem_wait_ld();                     // slab sl is in r[i & 1]
+                        if (i + 1 < my_slabs) {
+                            if ((sl + HALVES) * SLAB < width) issue_ld(sl + HALVES, (i & 1) ^ 1);   // streams in meanwhile
+                        } else {
+                            release_acc();
+                        }
+                        if (sl * SLAB < width) {
+                            process(sl, r[i & 1]);
+                        } else {
+                            // slab beyond the tail tile: no columns, but the buffer rotation, the residual barrier
+                            // phases and the bulk-group count stay those of a full tile
+                            const uint32_t ob = g % N_OUT;
+                            if (prm.has_res) ptx::mbar_wait(b_res_w + 8 * ob, (g / N_OUT) & 1u, 5);
+                            __syncwarp();
+                            if (lane == 0) {
+                                ptx::bulk_commit();
+                                bulk_wait_read<C::ST_PENDING>();
+                                if (prm.has_res) prefetch_res(g + C::RES_AHEAD);
+                            }
+                            ++g;
+                        }
+                    }
                 }
             }
         }
@@ -583,7 +662,7 @@ struct Problem {
     void* out;
     int64_t out_str[3];
     int geglu;
-    int variant;               // bit 0: CTA pairs; bits 8..15: BN override (0 = auto)
+    int variant;               // bit 0: CTA pairs; bit 1: no tail tiles; bits 8..16: BN override (0 = auto)
     const char* what;
 };
 
@@ -625,7 +704,10 @@ static int launch_cfg(const Problem& pb, Params prm, int b1, int b2, int b3, cud
             mr = mo;
         }
     }
-    prm.n_tiles = (int)(pb.N / C::OUT_COLS);
+    prm.n_tiles = (int)((pb.N + C::OUT_COLS - 1) / C::OUT_COLS);
+    prm.tail_cols = (int)(pb.N % C::OUT_COLS);
+    MVOC_REQUIRE(prm.tail_cols == 0 || (C::kEpi == EPI_LINEAR && prm.tail_cols % 64 == 0),
+                 MVOC_ERR_UNSUPPORTED, "%s: N=%lld does not tile by %d columns", what, (long long)pb.N, C::OUT_COLS);
     const int64_t m_tiles = (int64_t)prm.t1 * prm.t2 * ((pb.d3 + b3 - 1) / b3);
     const int64_t units = C::kTwoCta ? (m_tiles + 1) / 2 : m_tiles;
     const int64_t total = units * prm.n_tiles;
@@ -635,7 +717,7 @@ static int launch_cfg(const Problem& pb, Params prm, int b1, int b2, int b3, cud
     int64_t ctas = C::kTwoCta ? 2 * (total < sms / 2 ? total : sms / 2) : (total < sms ? total : sms);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)ctas);
-    cfg.blockDim = dim3(THREADS);
+    cfg.blockDim = dim3(C::THREADS);
     cfg.dynamicSmemBytes = C::alloc;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -695,12 +777,11 @@ static int run(const Problem& pb, cudaStream_t stream) {
     prm.bias = pb.bias;
     prm.has_res = pb.residual != nullptr;
     prm.gate_off = (int)pb.N;
-    prm.dbg = (pb.variant >> 20) & 3;
-    // Tile width and CTA mode.  Measured on B200 (profiles/r02_gemm_check_time_*.txt): a K chunk of 64 costs about
-    // 256 + 2 BN clocks on one CTA and 160 + 2 BN on a CTA pair (two 128-row tiles), so wide tiles win — until the
-    // problem has fewer tiles than the chip has SMs (the low-resolution levels, and every level once the frames are
-    // sharded over 8 GPUs), where narrower tiles and single CTAs fill more SMs.  Pick the cheapest of
-    // waves x chunk cost; variant bit 0 allows CTA pairs, bits 8.. force a width.
+    prm.dbg = (pb.variant >> 20) & 15;
+    // Tile width and CTA mode.  Wide tiles win (chunk_cost above) — until the problem has fewer tiles than the chip
+    // has SMs (the low-resolution levels, and every level once the frames are sharded over 8 GPUs), where narrower
+    // tiles and single CTAs fill more SMs.  Pick the cheapest of
+    // waves x chunk cost; variant bit 0 allows CTA pairs, bit 1 forbids a narrower tail tile, bits 8.. force a width.
     const int forced = (pb.variant >> 8) & 0x1ff;
     const bool allow_pair = (pb.variant & 1) != 0;
     const int64_t m_tiles = (int64_t)prm.t1 * prm.t2 * ((pb.d3 + b3 - 1) / b3);
@@ -709,19 +790,28 @@ static int run(const Problem& pb, cudaStream_t stream) {
     const int widths_geglu[2] = {256, 128};
     const int* widths = pb.geglu ? widths_geglu : widths_lin;
     const int n_widths = pb.geglu ? 2 : 5;
+    const bool allow_tail = (pb.variant & 2) == 0;   // variant bit 1: only widths that divide N (A/B switch)
     int BN = 0;
     bool two = false;
     double best = 0.0;
     for (int i = 0; i < n_widths; ++i) {
         const int w = widths[i];
         const int out_cols = pb.geglu ? w / 2 : w;
-        if (pb.N % out_cols != 0 || (forced && forced != w)) continue;
-        const int64_t n_tiles = pb.N / out_cols;
+        if (forced && forced != w) continue;
+        // a narrower LAST column tile (multiple of 64 columns) lets 256-wide tiles cover N = 640, 1920, 320 ...
+        const int tail = (int)(pb.N % out_cols);
+        if (tail != 0 && (pb.geglu || !allow_tail || w % 64 != 0 || tail % 64 != 0)) continue;
+        const int64_t n_full = pb.N / out_cols;
+        const int64_t n_tiles = n_full + (tail ? 1 : 0);
         for (int pair = allow_pair ? 1 : 0; pair >= 0; --pair) {
-            const int64_t units = pair ? ((m_tiles + 1) / 2) * n_tiles : m_tiles * n_tiles;
+            const int64_t units = (pair ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
             const int64_t slots = pair ? sms / 2 : sms;
             const double waves = (double)((units + slots - 1) / slots);
-            const double cost = waves * ((pair ? 160.0 : 256.0) + 2.0 * w);
+            // a pair tile covers two row tiles; the tail tile still fills a full-width weight box
+            const double per_tile = ((double)n_full * chunk_cost(w, pair != 0) +
+                                     (tail ? 0.5 * (chunk_cost(tail, pair != 0) + chunk_cost(w, pair != 0)) : 0.0)) /
+                                    (double)n_tiles;
+            const double cost = waves * per_tile;
             if (BN == 0 || cost < best * 0.999) best = cost, BN = w, two = pair != 0;
         }
     }

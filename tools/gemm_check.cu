@@ -195,7 +195,10 @@ static int section_linear(int variant) {
     const int64_t cases[][6] = {{128, 64, 64, 0, 0, 0},     {256, 64, 64, 0, 0, 0},      {1000, 320, 320, 0, 0, 0},
                                 {4096, 320, 960, 0, 0, 0},  {777, 640, 640, 0, 0, 0},    {2048, 1280, 1280, 0, 0, 0},
                                 {300, 128, 192, 64, 128, 0}, {5000, 320, 1280, 0, 0, 128}, {11600, 1024, 640, 0, 0, 0},
-                                {40960, 320, 320, 0, 0, 0}, {20000, 1280, 320, 0, 0, 64}, {640, 2560, 1280, 0, 0, 0}};
+                                {40960, 320, 320, 0, 0, 0}, {20000, 1280, 320, 0, 0, 64}, {640, 2560, 1280, 0, 0, 0},
+                                // a narrower tail tile after the full-width ones: 256+64, 2x256+128, 3x256+192, 192+128, 2x192+64
+                                {3000, 320, 320, 0, 0, 256}, {2500, 640, 640, 0, 0, 256}, {1500, 320, 960, 0, 0, 256},
+                                {1300, 256, 320, 0, 64, 192}, {900, 128, 448, 64, 0, 192}, {70000, 320, 640, 0, 0, 256}};
     int bad = 0;
     for (auto& c : cases)
         for (int mode = 0; mode < 3; ++mode) {   // 0: plain, 1: + bias, 2: + bias + residual
@@ -347,6 +350,51 @@ static int section_port(int variant) {
     return 0;
 }
 
+// tile-width experiment: ONE problem whose Cout every width divides, each width forced in turn, with and without
+// the TMA refills (variant bits 20 / 21) — separates the tensor pipe's rate at N = BN from the fill traffic.
+static int section_width(int variant) {
+    const int N = 80, Hh = 32, W = 32, ci = 640, co = 3840;
+    const size_t px = (size_t)N * Hh * W;
+    bf16 *x = dev_random(px * ci, 1.0f), *wt = dev_random((size_t)9 * co * ci, 0.02f), *bias = dev_random(co, 1.0f),
+         *y = dev_alloc<bf16>(px * co);
+    const double fl = 2.0 * px * co * (double)ci * 9;
+    const int widths[] = {256, 192, 160, 128, 64};
+    for (int bn : widths)
+        for (int dbg = 0; dbg < 4; dbg += 3) {
+            const int v = variant | (bn << 8) | (dbg << 20);
+            const float t = time_ms([&] { mvoc_conv3x3_nhwc(x, wt, bias, nullptr, nullptr, nullptr, 0, y, N, Hh, W, ci, co, MVOC_BF16, v, nullptr); }, 3);
+            printf("conv %dx%dx%d %4d->%4d v%d bn=%3d %s: %.3f ms  %.0f TF/s\n", N, Hh, W, ci, co, variant, bn,
+                   dbg ? "no refills" : "normal    ", t, fl / t / 1e9);
+            fflush(stdout);
+        }
+    cudaFree(x), cudaFree(wt), cudaFree(bias), cudaFree(y);
+    return 0;
+}
+
+// short-K Linears (HBM / epilogue bound): the same launch with parts of the kernel switched off (variant bits 20..23)
+static int section_short(int variant) {
+    const int64_t lins[][4] = {{327680, 320, 320, 0}, {327680, 320, 320, 1}, {327680, 320, 960, 0}, {81920, 640, 640, 1}};
+    const int dbgs[] = {0, 3, 4, 7, 8, 11};
+    for (auto& c : lins) {
+        const int64_t M = c[0];
+        const int K = (int)c[1], N = (int)c[2];
+        bf16 *x = dev_random((size_t)M * K, 1.0f), *w = dev_random((size_t)N * K, 0.05f), *bias = dev_random(N, 1.0f),
+             *res = c[3] ? dev_random((size_t)M * N, 1.0f) : nullptr, *y = dev_alloc<bf16>((size_t)M * N);
+        const double bytes = ((double)M * K + (double)M * N * (c[3] ? 2 : 1) + (double)N * K) * 2;
+        for (int dbg : dbgs) {
+            if ((dbg & 8) && c[3]) continue;
+            const int v = variant | (dbg << 20);
+            const float t = time_ms([&] { mvoc_linear(x, w, bias, res, y, M, K, N, K, N, N, MVOC_BF16, v, nullptr); }, 5);
+            printf("linear M=%lld K=%d N=%d%s v%d %s%s%s: %.3f ms  %.0f GB/s of algorithmic bytes\n", (long long)M, K, N,
+                   c[3] ? " +res" : "", variant, (dbg & 3) == 3 ? "no-refill " : "", (dbg & 4) ? "no-store " : "",
+                   (dbg & 8) ? "no-epilogue " : "", t, bytes / t / 1e6);
+            fflush(stdout);
+        }
+        cudaFree(x), cudaFree(w), cudaFree(bias), cudaFree(res), cudaFree(y);
+    }
+    return 0;
+}
+
 static int section_time(int variant) {
     // the UNet's shapes at config 2 (80 frames): l0 64x64 C320, l1 32x32 C640, l2 16x16 C1280, l3 8x8 C1280
     const int convs[][5] = {{80, 64, 64, 320, 320},   {80, 64, 64, 640, 320},   {80, 64, 64, 960, 320},  {80, 32, 32, 640, 640},
@@ -358,17 +406,16 @@ static int section_time(int variant) {
         bf16 *x = dev_random(px * ci, 1.0f), *wt = dev_random((size_t)9 * co * ci, 0.02f), *bias = dev_random(co, 1.0f),
              *y = dev_alloc<bf16>(px * co);
         const double fl = 2.0 * px * co * (double)ci * 9;
-        const int bns[] = {0, 128, 64};
+        // auto, auto restricted to widths that divide Cout (variant bit 1), then forced widths (a narrower tail tile
+        // covers the remainder where the width does not divide Cout)
+        const int bns[] = {0, -1, 256, 192, 128};
         for (int bn : bns) {
-            if (bn && co % bn) continue;
-            const int v = variant | (bn << 8);
+            const int v = bn < 0 ? (variant | 2) : (variant | (bn << 8));
             const int rc = mvoc_conv3x3_nhwc(x, wt, bias, nullptr, nullptr, nullptr, 0, y, N, Hh, W, ci, co, MVOC_BF16, v, nullptr);
-            if (rc) {
-                printf("conv rc=%d %s\n", rc, mvoc_last_error());
-                continue;
-            }
+            if (rc) continue;   // this width cannot tile Cout
             const float t = time_ms([&] { mvoc_conv3x3_nhwc(x, wt, bias, nullptr, nullptr, nullptr, 0, y, N, Hh, W, ci, co, MVOC_BF16, v, nullptr); }, 5);
-            printf("conv %dx%dx%d %4d->%4d bn=%3d v%d : %.3f ms  %.0f TF/s\n", N, Hh, W, ci, co, bn, variant, t, fl / t / 1e9);
+            printf("conv %dx%dx%d %4d->%4d bn=%3d%s v%d : %.3f ms  %.0f TF/s\n", N, Hh, W, ci, co, bn < 0 ? 0 : bn,
+                   bn < 0 ? " exact widths" : "", variant, t, fl / t / 1e9);
             fflush(stdout);
         }
         cudaFree(x), cudaFree(wt), cudaFree(bias), cudaFree(y);
@@ -384,18 +431,14 @@ static int section_time(int variant) {
              *res = c[3] ? dev_random((size_t)M * N, 1.0f) : nullptr, *y = dev_alloc<bf16>((size_t)M * N);
         const double fl = 2.0 * M * (double)K * N;
         const double bytes = ((double)M * K + (double)M * N * (c[3] ? 2 : 1) + (double)N * K) * 2;
-        const int bns[] = {0, 128};
+        const int bns[] = {0, -1, 256, 192};
         for (int bn : bns) {
-            if (bn && N % bn) continue;
-            const int v = variant | (bn << 8);
+            const int v = bn < 0 ? (variant | 2) : (variant | (bn << 8));
             const int rc = mvoc_linear(x, w, bias, res, y, M, K, N, K, N, N, MVOC_BF16, v, nullptr);
-            if (rc) {
-                printf("linear rc=%d %s\n", rc, mvoc_last_error());
-                continue;
-            }
+            if (rc) continue;
             const float t = time_ms([&] { mvoc_linear(x, w, bias, res, y, M, K, N, K, N, N, MVOC_BF16, v, nullptr); }, 5);
-            printf("linear M=%lld K=%d N=%d%s bn=%3d v%d : %.3f ms  %.0f TF/s  %.0f GB/s\n", (long long)M, K, N,
-                   c[3] ? " +res" : "", bn, variant, t, fl / t / 1e9, bytes / t / 1e6);
+            printf("linear M=%lld K=%d N=%d%s bn=%3d%s v%d : %.3f ms  %.0f TF/s  %.0f GB/s\n", (long long)M, K, N,
+                   c[3] ? " +res" : "", bn < 0 ? 0 : bn, bn < 0 ? " exact widths" : "", variant, t, fl / t / 1e9, bytes / t / 1e6);
             fflush(stdout);
         }
         cudaFree(x), cudaFree(w), cudaFree(bias), cudaFree(res), cudaFree(y);
@@ -419,10 +462,13 @@ static int section_time(int variant) {
         const size_t rows = (size_t)B * T * S;
         bf16 *x = dev_random(rows * C, 1.0f), *wt = dev_random((size_t)3 * C * C, 0.02f), *bias = dev_random(C, 1.0f),
              *y = dev_alloc<bf16>(rows * C);
-        const float t = time_ms([&] { mvoc_temporal_conv3(x, wt, bias, nullptr, y, B, T, S, C, C, MVOC_BF16, variant, nullptr); }, 5);
-        printf("tconv B=%d T=%d S=%lld C=%d v%d : %.3f ms  %.0f TF/s\n", B, T, (long long)S, C, variant, t,
-               2.0 * rows * C * (double)C * 3 / t / 1e9);
-        fflush(stdout);
+        for (int notail = 0; notail < 2; ++notail) {
+            const int v = variant | (notail << 1);
+            const float t = time_ms([&] { mvoc_temporal_conv3(x, wt, bias, nullptr, y, B, T, S, C, C, MVOC_BF16, v, nullptr); }, 5);
+            printf("tconv B=%d T=%d S=%lld C=%d v%d %s: %.3f ms  %.0f TF/s\n", B, T, (long long)S, C, variant,
+                   notail ? "exact widths" : "auto        ", t, 2.0 * rows * C * (double)C * 3 / t / 1e9);
+            fflush(stdout);
+        }
         cudaFree(x), cudaFree(wt), cudaFree(bias), cudaFree(y);
     }
     cudaError_t e = cudaDeviceSynchronize();
@@ -479,6 +525,8 @@ int main(int argc, char** argv) {
     else if (!strcmp(what, "geglu")) bad = section_geglu(variant);
     else if (!strcmp(what, "time")) bad = section_time(variant);
     else if (!strcmp(what, "port")) bad = section_port(variant);
+    else if (!strcmp(what, "width")) bad = section_width(variant);
+    else if (!strcmp(what, "short")) bad = section_short(variant);
     else {
         printf("usage: gemm_check linear|conv|tconv|geglu|time [variant]\n");
         return 2;

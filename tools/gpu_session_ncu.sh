@@ -2,6 +2,12 @@
 # ncu --set full captures of every kernel family at its benchmark shape + the launch list of one timed step.
 set -u
 TAG="${1:-r02}"
+if [ -x tools/gemm_check ]; then
+    echo "== GEMM tile-width experiment" | tee -a "gpurun_out/${TAG}_ncu_session.log"
+    mkdir -p gpurun_out
+    timeout 120 tools/gemm_check width 1 > "gpurun_out/${TAG}_gemm_width_pairs.txt" 2>&1
+    timeout 120 tools/gemm_check width 0 > "gpurun_out/${TAG}_gemm_width_single.txt" 2>&1
+fi
 OUT=gpurun_out
 mkdir -p "$OUT"
 cap() {  # cap <name> <kernel regex>
@@ -9,6 +15,13 @@ cap() {  # cap <name> <kernel regex>
     timeout --signal=TERM --kill-after=10 150 ncu --set full --clock-control none --import-source on -k "regex:$2" -s 2 -c 1 -f \
         -o "$OUT/${TAG}_ncu_$1" python tools/ncu_kernels.py "$1" > "$OUT/${TAG}_ncu_$1.log" 2>&1
     echo "   exit $?" | tee -a "$OUT/${TAG}_ncu_session.log"
+    # the reports (tens of MB each with sources) stay on the box: gpurun_out/ carries <= 64 MiB back
+    if [ -f "$OUT/${TAG}_ncu_$1.ncu-rep" ]; then
+        python tools/ncu_summary.py "$OUT/${TAG}_ncu_$1.ncu-rep" > "$OUT/${TAG}_ncu_$1_summary.txt" 2>&1
+        ncu -i "$OUT/${TAG}_ncu_$1.ncu-rep" --page details --csv > "$OUT/${TAG}_ncu_$1_details.csv" 2>/dev/null
+        ls -la "$OUT/${TAG}_ncu_$1.ncu-rep" >> "$OUT/${TAG}_ncu_session.log"
+        rm -f "$OUT/${TAG}_ncu_$1.ncu-rep"
+    fi
 }
 cap attn attn_fwd_kernel
 cap attn_pair attn_fwd_kernel
@@ -27,4 +40,7 @@ echo "== launch list of one timed step (eager)" | tee -a "$OUT/${TAG}_ncu_sessio
 timeout --signal=TERM --kill-after=20 900 ncu --metrics gpu__time_duration.sum --clock-control none --nvtx \
     --nvtx-include "mvoc_timed_region/" --csv --log-file "$OUT/${TAG}_launches_timed_step.csv" \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-graphs > "$OUT/${TAG}_launches_bench.log" 2>&1
+echo "   exit $?" | tee -a "$OUT/${TAG}_ncu_session.log"
+echo "== N=1 bench, K=5 (for kernels.top)" | tee -a "$OUT/${TAG}_ncu_session.log"
+timeout --signal=TERM --kill-after=20 400 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > "$OUT/${TAG}_bench_n1_k5.log" 2>&1
 echo "   exit $?" | tee -a "$OUT/${TAG}_ncu_session.log"
