@@ -252,6 +252,34 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x + 0.5f * fabsf(x) * erf_abs;          // 0.5 x (1 + sign(x) erf(|x| / sqrt 2))
 }
 
+// The same for a pair of gates on the packed fp32x2 pipe (FFMA2 / FMUL2: two lanes per issue slot) — the GEGLU
+// epilogue is bounded by instruction issue, and 12 of gelu_erf's 16 arithmetic instructions are FMA-class.
+// v2 (a pair of values) is multiplied by gelu(g2) and returned.
+__device__ __forceinline__ uint64_t mul_gelu_erf2(uint64_t v2, uint64_t g2) {
+    float g0, g1;
+    ptx::unpack2(g2, g0, g1);
+    const uint64_t ax = ptx::pack2(fabsf(g0), fabsf(g1));
+    const uint64_t t = ptx::mul2(ax, ptx::pack2(0.70710678118654752f, 0.70710678118654752f));
+    const uint64_t d = ptx::fma2(ptx::pack2(0.3275911f, 0.3275911f), t, ptx::pack2(1.0f, 1.0f));
+    float d0, d1, k0, k1;
+    ptx::unpack2(d, d0, d1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(k0) : "f"(d0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(k1) : "f"(d1));
+    const uint64_t k = ptx::pack2(k0, k1);
+    uint64_t p = ptx::fma2(ptx::pack2(1.061405429f, 1.061405429f), k, ptx::pack2(-1.453152027f, -1.453152027f));
+    p = ptx::fma2(p, k, ptx::pack2(1.421413741f, 1.421413741f));
+    p = ptx::fma2(p, k, ptx::pack2(-0.284496736f, -0.284496736f));
+    p = ptx::fma2(p, k, ptx::pack2(0.254829592f, 0.254829592f));
+    const uint64_t ea = ptx::mul2(ptx::mul2(t, t), ptx::pack2(-1.4426950408889634f, -1.4426950408889634f));
+    float e0, e1;
+    ptx::unpack2(ea, e0, e1);
+    const uint64_t e = ptx::pack2(ptx::ex2_approx(e0), ptx::ex2_approx(e1));
+    const uint64_t erf_abs = ptx::sub2(ptx::pack2(1.0f, 1.0f), ptx::mul2(ptx::mul2(p, k), e));   // erf(|g| / sqrt 2)
+    const uint64_t half = ptx::pack2(0.5f, 0.5f);
+    const uint64_t gelu = ptx::fma2(ptx::mul2(ax, half), erf_abs, ptx::mul2(g2, half));
+    return ptx::mul2(v2, gelu);
+}
+
 // Instruction descriptor kind::f16: 16-bit inputs (kF16 ? fp16 : bf16), fp32 accumulation, A and B K-major.
 __host__ __device__ constexpr uint32_t idesc_16(int M, int N, bool f16) {
     return (1u << 4) | ((f16 ? 0u : 1u) << 7) | ((f16 ? 0u : 1u) << 10) | ((uint32_t)(N >> 3) << 17) |
@@ -509,7 +537,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant_
                         for (int e = 0; e < 8; ++e) gv[e] = __uint_as_float(gt[c * 8 + e]);
                         if (bias) add8<T>(gv, ldg16_nc(bias + prm.gate_off + col0 + sl * SLAB + c * 8));
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) f[e] *= gelu_erf(gv[e]);
+                        for (int e = 0; e < 8; e += 2)
+                            ptx::unpack2(mul_gelu_erf2(ptx::pack2(f[e], f[e + 1]), ptx::pack2(gv[e], gv[e + 1])), f[e],
+                                         f[e + 1]);
                     }
                     const uint32_t addr = sbuf + (((uint32_t)c ^ sw) << 4);
                     if (prm.has_res) add8<T>(f, lds16(addr));
