@@ -121,7 +121,9 @@ def test_host_invert_loop_vs_oracle(emulated_ops, tmp_path):
     assert sorted(saved) == sorted(ref) == [1, 3, 5]
     for t in saved:
         assert rel_l2(saved[t], ref[t]) <= TOL
-        assert torch.equal(load_ddim_latents_at_t(t, str(tmp_path)), saved[t])
+        # the file holds the reference's wire dtype (its fp16 pipeline latents, pipeline_i2vgen_xl.py:1990-1993)
+        on_disk = load_ddim_latents_at_t(t, str(tmp_path))
+        assert on_disk.dtype == torch.float16 and torch.equal(on_disk, saved[t].to(torch.float16))
 
 
 # ------------------------------------------------------------------ frame-parallel (gloo, world_size 2)
