@@ -329,6 +329,7 @@ def run_mvoc(args):
     ms_step = ms_total / K
 
     # ---- timed region 2: end to end through the pipeline API with host buffers ------------------
+    loop(0, 1, host_io=True)      # untimed: first-use pinned allocations of the host path
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
@@ -533,10 +534,11 @@ def run_inversion(args, wl, par, dev, rank, world, local):
         vids.append((inv["latents"].to(dev), pe, ie, il, fps, Conditioning(pe, ie, il, il, fps)))
     K, W = min(args.steps, wl.inversion_steps), max(args.warmup, 0)
 
+    pinned = [torch.empty(v[0].shape, dtype=v[0].dtype).pin_memory() for v in vids]   # once, outside the timing
+
     def steps(n, host_io=False):
         out = None
-        for lat, pe, ie, il, fps, cond in vids:
-            host = torch.empty(lat.shape, dtype=lat.dtype).pin_memory() if host_io else None
+        for (lat, pe, ie, il, fps, cond), host in zip(vids, pinned):
             x = host.copy_(lat.cpu()).to(dev, non_blocking=True) if host_io else lat.clone()
             pipe.invert(x, pe, ie, il, fps, num_inference_steps=wl.inversion_steps, max_steps=n, keep=False, cond=cond,
                         on_step=(lambda t, z: host.copy_(z, non_blocking=False)) if host_io else None)

@@ -268,7 +268,7 @@ class I2VGenXLPipeline:
         unet_in = self.static_input((nb,) + tuple(latents.shape[1:]), latents.device)
         objs = torch.empty((n_obj,) + tuple(latents.shape[1:]), dtype=torch.float32, device=latents.device)
         bg = torch.empty(tuple(latents.shape[1:]), dtype=torch.float32, device=latents.device)
-        host_out = torch.empty(latents.shape, dtype=latents.dtype).pin_memory() if host_io else None
+        host_out = self._pinned_out(latents) if host_io else None
         for i, t in enumerate(timesteps):
             if i < start_step:
                 continue
@@ -297,6 +297,18 @@ class I2VGenXLPipeline:
             if callback is not None:
                 callback(i, t, latents)
         return latents
+
+    def _pinned_out(self, like: torch.Tensor) -> torch.Tensor:
+        """Pinned host buffer for the per-step read-back, allocated once per shape (cudaHostAlloc takes tens of
+        milliseconds when several ranks call it at once — not something to pay inside every loop call)."""
+        key = (tuple(like.shape), like.dtype)
+        buf = getattr(self, "_host_out", {}).get(key)
+        if buf is None:
+            buf = torch.empty(like.shape, dtype=like.dtype).pin_memory()
+            if not hasattr(self, "_host_out"):
+                self._host_out = {}
+            self._host_out[key] = buf
+        return buf
 
     # ------------------------------------------------------------------ inversion
     @torch.no_grad()
