@@ -242,6 +242,13 @@ int mvoc_layernorm(const void* x, void* y, const void* gamma, const void* beta, 
 int mvoc_geglu(const void* x, void* y, int64_t M, int F, int dtype, void* stream);
 
 /*
+ * Nearest-neighbour 2x upsampling of a channels-last activation x [N, H, W, C] -> y [N, 2H, 2W, C]: the
+ * F.interpolate(scale_factor=2.0, mode="nearest") of diffusers' Upsample2D in the up blocks
+ * (i2vgen-xl/pipelines/pipeline_i2vgen_xl.py:318-350 -> UpBlock3D / CrossAttnUpBlock3D upsamplers).  C % 8 == 0.
+ */
+int mvoc_upsample_nearest2x_nhwc(const void* x, void* y, int64_t N, int H, int W, int C, int dtype, void* stream);
+
+/*
  * ---- dense work on tcgen05 tensor cores (csrc/gemm_tc.cu) ------------------------------------------------
  * One persistent implicit-GEMM kernel: 128-row activation tiles are TMA boxes of the channels-last tensor
  * (shifted per filter tap, zero-filled outside = the padding), weights are K-major [tap, Cout, Cin], fp32

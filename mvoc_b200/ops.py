@@ -533,6 +533,23 @@ def geglu(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     return out
 
 
+def upsample_nearest2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [N, H, W, C] channels-last -> [N, 2H, 2W, C], nearest neighbour (Upsample2D of the up blocks)."""
+    _need_cuda(x, out)
+    if x.dim() != 4 or not x.is_contiguous():
+        raise ValueError("upsample_nearest2x: x must be a contiguous [N, H, W, C] tensor")
+    N, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((N, 2 * H, 2 * W, C), dtype=x.dtype, device=x.device)
+    elif tuple(out.shape) != (N, 2 * H, 2 * W, C) or not out.is_contiguous() or out.dtype != x.dtype:
+        raise ValueError("upsample_nearest2x: out must be a contiguous [N, 2H, 2W, C] tensor of x's dtype")
+    with _Timed(("upsample2x", N, H, W, C), 5.0 * x.numel() * x.element_size()):
+        _cabi.check(_cabi.load().mvoc_upsample_nearest2x_nhwc(x.data_ptr(), out.data_ptr(), N, H, W, C, _dt(x), _stream()),
+                    "mvoc_upsample_nearest2x_nhwc")
+    _count()
+    return out
+
+
 def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Row-wise LayerNorm over the last dim of a contiguous [..., C] tensor (warp per row)."""

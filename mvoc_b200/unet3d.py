@@ -572,6 +572,10 @@ class Upsample2D(nn.Module):
         self.conv = nn.Conv2d(channels, channels, 3, padding=1)
 
     def forward(self, x, output_size=None, scale: float = 1.0):
+        n, h, w, c = x.shape
+        if (output_size is None or tuple(output_size) == (2 * h, 2 * w)) and c % 8 == 0 and x.is_contiguous() \
+                and x.dtype in (torch.bfloat16, torch.float16):
+            return conv_nhwc(ops.upsample_nearest2x(x), self.conv)               # the library's kernel
         xc = x.permute(0, 3, 1, 2)                                              # channels_last view
         if output_size is None:
             xc = F.interpolate(xc, scale_factor=2.0, mode="nearest")

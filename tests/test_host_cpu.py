@@ -69,6 +69,10 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc == -2 and b"multiple of 64" in lib.mvoc_last_error()
     rc = lib.mvoc_linear(16, 16, None, None, 16, 128, 64, 64, 64, 0, 64, 2, 0, None)
     assert rc == -2 and b"dtype" in lib.mvoc_last_error()                           # fp32 storage is not supported
+    rc = lib.mvoc_upsample_nearest2x_nhwc(16, 16, 2, 8, 8, 60, 0, None)
+    assert rc == -2 and b"multiple of 8" in lib.mvoc_last_error()
+    rc = lib.mvoc_upsample_nearest2x_nhwc(16, None, 2, 8, 8, 64, 0, None)
+    assert rc == -1 and b"null pointer" in lib.mvoc_last_error()
 
 
 def test_product_ops_refuse_cpu_tensors():

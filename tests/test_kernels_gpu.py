@@ -464,6 +464,24 @@ def test_layernorm_vs_torch(cuda_device, M, C):
     assert torch.equal(out, again)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("N,H,W,C", [(80, 32, 32, 640), (5, 8, 8, 1280), (3, 11, 20, 64), (1, 1, 1, 8), (2, 7, 3, 328)])
+def test_upsample_nearest2x_is_exact(cuda_device, N, H, W, C, dtype):
+    """Upsample2D's F.interpolate(scale_factor=2, mode='nearest') on channels-last rows: a pure copy, bit exact."""
+    from mvoc_b200 import ops
+
+    torch.manual_seed(N + H + W + C)
+    x = torch.randn(N, H, W, C).to(dtype).to(cuda_device)
+    ref = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2).float(), scale_factor=2.0, mode="nearest")
+    ref = ref.permute(0, 2, 3, 1).to(dtype)
+    out = ops.upsample_nearest2x(x)
+    torch.cuda.synchronize()
+    assert out.shape == (N, 2 * H, 2 * W, C) and out.is_contiguous()
+    assert torch.equal(out, ref)
+    with pytest.raises(ValueError):
+        ops.upsample_nearest2x(x[0])                     # not [N, H, W, C]
+
+
 # ------------------------------------------------------------------ dense work on tcgen05 (csrc/gemm_tc.cu)
 GEMM_VARIANTS = [0, 1]      # one CTA per tile / CTA pairs (cta_group::2)
 
