@@ -307,9 +307,12 @@ int mvoc_linear_geglu(const void* x, const void* w, const void* bias, void* out,
  * rank's buffer (pack + transfer + unpack in one pass), then publishes a per-site epoch in every peer's flag row;
  * mvoc_exchange_wait spins until all sources have published.  Epochs live in device memory: CUDA-graph safe.
  * `site`: index of the exchange within one forward (each site owns a flag row), < mvoc_exchange_max_sites().
+ * `site | MVOC_EXCHANGE_WAIT_FUSED`: the put kernel itself also waits for the peers (its last CTA spins on this
+ * rank's flag row after publishing), so that no separate mvoc_exchange_wait launch is needed for the site.
  * peer_bases: HOST array of `world` device pointers (the arenas as mapped into THIS process; entry `rank` is the
  * local arena).  dst_offset: byte offset of the destination buffer inside every arena (>= header bytes).
  */
+#define MVOC_EXCHANGE_WAIT_FUSED (1 << 30)
 int64_t mvoc_exchange_header_bytes(void);
 int mvoc_exchange_max_sites(void);
 int mvoc_exchange_arena_create(int64_t bytes, void** base, void* ipc_handle64);

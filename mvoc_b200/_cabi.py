@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libm
 MVOC_BF16, MVOC_F16, MVOC_F32 = 0, 1, 2
 MVOC_MASK_U8, MVOC_MASK_F32 = 0, 1
 MVOC_MAX_OBJECTS = 8
+MVOC_EXCHANGE_WAIT_FUSED = 1 << 30
 
 
 class MvocLibraryError(RuntimeError):

@@ -13,6 +13,8 @@
 //                collapse into one pass); the last CTA to finish publishes this rank's epoch in every peer's flag
 //                row with a system-scope release store
 //   wait kernel  one warp spins (system-scope acquire loads) until every source rank has published the epoch
+//                (or, with MVOC_EXCHANGE_WAIT_FUSED, the put kernel's last CTA does the same after publishing:
+//                one launch per exchange instead of two)
 // Epochs live in device memory (one counter per exchange site), so a captured CUDA graph replays correctly.
 #include "common.cuh"
 
@@ -24,6 +26,8 @@ constexpr int MAX_SITES = 1024;
 // arena header: [0, 64 KB): flags[site][src rank] (uint32) written by peers; [64 KB, 68 KB): this rank's own epoch
 // counters per site; [68 KB, 72 KB): CTA arrival counters per site; payload from 128 KB on.
 constexpr int64_t HDR_FLAGS = 0, HDR_EPOCH = 65536, HDR_ARRIVE = 65536 + 4096, HDR_BYTES = 131072;
+
+constexpr int SITE_MASK = MVOC_EXCHANGE_WAIT_FUSED - 1;   // the site argument may carry MVOC_EXCHANGE_WAIT_FUSED
 
 struct Peers {
     void* base[MAX_RANKS];
@@ -40,7 +44,10 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 
 // After this CTA's peer stores: fence, count the CTA in; the last one bumps this rank's epoch for the site and
 // publishes it in flags[site][rank] of every peer.
-__device__ __forceinline__ void publish(const Peers& peers, int rank, int world, int site) {
+// With `wait_here` the same thread then waits until every peer has published the site in THIS rank's flag row: the
+// put and the wait of an exchange are one launch (all of this rank's puts are issued by then, so nobody can
+// dead-lock on a CTA that is still moving data).
+__device__ __forceinline__ void publish(const Peers& peers, int rank, int world, int site, bool wait_here) {
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -57,6 +64,20 @@ __device__ __forceinline__ void publish(const Peers& peers, int rank, int world,
                 unsigned* flag = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(peers.base[d]) + HDR_FLAGS) +
                                  (size_t)site * MAX_RANKS + rank;
                 st_release_sys(flag, e);
+            }
+            if (wait_here) {
+                const unsigned* row = reinterpret_cast<const unsigned*>(mine + HDR_FLAGS) + (size_t)site * MAX_RANKS;
+                for (int d = 0; d < world; ++d) {
+                    unsigned spins = 0;
+                    while ((int)(ld_acquire_sys(row + d) - e) < 0) {
+                        __nanosleep(64);
+                        if (++spins > (1u << 25)) {
+                            printf("mvoc exchange put+wait: site %d rank-slot %d stuck at %u (want %u)\n", site, d,
+                                   ld_acquire_sys(row + d), e);
+                            __trap();
+                        }
+                    }
+                }
             }
         }
     }
@@ -83,7 +104,7 @@ __global__ void __launch_bounds__(256) put_pixel_shards_kernel(const Vec16* __re
         Vec16* dst = reinterpret_cast<Vec16*>(reinterpret_cast<char*>(peers.base[d]) + dst_off) + drow * row_vecs + v;
         st_stream16(dst, ld_stream16(x + i));
     }
-    publish(peers, rank, world, site);
+    publish(peers, rank, world, site & SITE_MASK, (site & MVOC_EXCHANGE_WAIT_FUSED) != 0);
 }
 
 // pixel shards -> frame shards.  Local y [b, T, sp, C]; destination rank d owns frames [d * tl, (d + 1) * tl) and
@@ -107,7 +128,7 @@ __global__ void __launch_bounds__(256) put_frame_shards_kernel(const Vec16* __re
         Vec16* dst = reinterpret_cast<Vec16*>(reinterpret_cast<char*>(peers.base[d]) + dst_off) + drow * row_vecs + v;
         st_stream16(dst, ld_stream16(y + i));
     }
-    publish(peers, rank, world, site);
+    publish(peers, rank, world, site & SITE_MASK, (site & MVOC_EXCHANGE_WAIT_FUSED) != 0);
 }
 
 // all-gather of a small buffer (GroupNorm partial statistics of a pixel shard): slot `rank` of every peer's
@@ -121,7 +142,7 @@ __global__ void __launch_bounds__(256) put_allgather_kernel(const Vec16* __restr
         Vec16* dst = reinterpret_cast<Vec16*>(reinterpret_cast<char*>(peers.base[d]) + dst_off) + (int64_t)rank * n_vec + j;
         st_stream16(dst, ld_global16(src + j));
     }
-    publish(peers, rank, world, site);
+    publish(peers, rank, world, site & SITE_MASK, (site & MVOC_EXCHANGE_WAIT_FUSED) != 0);
 }
 
 __global__ void wait_kernel(const char* mine, int world, int site) {
@@ -141,7 +162,8 @@ __global__ void wait_kernel(const char* mine, int world, int site) {
     }
 }
 
-static int check_common(const char* what, void* const* peer_bases, int rank, int world, int site) {
+static int check_common(const char* what, void* const* peer_bases, int rank, int world, int site_arg) {
+    const int site = site_arg & SITE_MASK;
     MVOC_REQUIRE(peer_bases != nullptr, MVOC_ERR_INVALID_ARG, "%s: null peer table", what);
     MVOC_REQUIRE(world >= 1 && world <= MAX_RANKS && rank >= 0 && rank < world, MVOC_ERR_INVALID_ARG,
                  "%s: rank %d of %d (at most %d ranks)", what, rank, world, MAX_RANKS);

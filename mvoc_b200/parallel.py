@@ -66,6 +66,10 @@ class PeerExchange:
             self.peer_bases[r] = p.value
             self._opened.append(p.value)
         self._mem = torch.as_tensor(_RawDeviceMemory(self.base, self.bytes), device=self.device)
+        # put + wait of an exchange as ONE launch (the put kernel's last CTA waits for the peers); MVOC_EXCHANGE_WAIT=
+        # separate keeps the two-launch form (A/B switch)
+        self.fused_wait = os.environ.get("MVOC_EXCHANGE_WAIT", "fused") != "separate"
+        self._flag = _cabi.MVOC_EXCHANGE_WAIT_FUSED if self.fused_wait else 0
         self.reset()
         dist.barrier(group=group)      # every arena is mapped everywhere before the first put
 
@@ -95,6 +99,16 @@ class PeerExchange:
     def _stream(self) -> int:
         return torch.cuda.current_stream().cuda_stream
 
+    def _wait(self, site: int) -> None:
+        """The data of every peer has arrived when this returns (in stream order)."""
+        from . import _cabi, ops
+
+        if self.fused_wait:            # the put kernel already waited
+            ops._count(1)
+            return
+        _cabi.check(self._lib.mvoc_exchange_wait(self.base, self.world, site, self._stream()), "mvoc_exchange_wait")
+        ops._count(2)
+
     def to_pixel_shards(self, x: torch.Tensor, b: int, tl: int, S: int, C: int) -> torch.Tensor:
         """x contiguous [b*tl, ..., C] (this rank's frames) -> [b*T, 1, S/P, C] (all frames, this rank's pixels)."""
         from . import _cabi, ops
@@ -104,10 +118,9 @@ class PeerExchange:
         site = self._next_site()
         with ops._Timed(("exchange", "to_pixel", b * tl, S, C), 2.0 * x.numel() * x.element_size()):
             _cabi.check(self._lib.mvoc_exchange_to_pixel_shards(x.data_ptr(), self.peer_bases, off, self.rank, P, b, tl,
-                                                                S, C, ops._dt(x), site, self._stream()),
+                                                                S, C, ops._dt(x), site | self._flag, self._stream()),
                         "mvoc_exchange_to_pixel_shards")
-            _cabi.check(self._lib.mvoc_exchange_wait(self.base, P, site, self._stream()), "mvoc_exchange_wait")
-        ops._count(2)
+            self._wait(site)
         return out
 
     def to_frame_shards(self, y: torch.Tensor, b: int, T: int, sp: int, C: int, h: int, w: int) -> torch.Tensor:
@@ -119,10 +132,9 @@ class PeerExchange:
         site = self._next_site()
         with ops._Timed(("exchange", "to_frame", b * T, sp, C), 2.0 * y.numel() * y.element_size()):
             _cabi.check(self._lib.mvoc_exchange_to_frame_shards(y.data_ptr(), self.peer_bases, off, self.rank, P, b, T, sp,
-                                                                C, ops._dt(y), site, self._stream()),
+                                                                C, ops._dt(y), site | self._flag, self._stream()),
                         "mvoc_exchange_to_frame_shards")
-            _cabi.check(self._lib.mvoc_exchange_wait(self.base, P, site, self._stream()), "mvoc_exchange_wait")
-        ops._count(2)
+            self._wait(site)
         return out
 
     def allgather(self, t: torch.Tensor) -> torch.Tensor:
@@ -134,10 +146,9 @@ class PeerExchange:
         off, out = self._alloc((P,) + tuple(t.shape), t.dtype)
         site = self._next_site()
         with ops._Timed(("exchange", "allgather", nbytes), float(nbytes) * P):
-            _cabi.check(self._lib.mvoc_exchange_allgather(t.data_ptr(), nbytes, self.peer_bases, off, self.rank, P, site,
-                                                          self._stream()), "mvoc_exchange_allgather")
-            _cabi.check(self._lib.mvoc_exchange_wait(self.base, P, site, self._stream()), "mvoc_exchange_wait")
-        ops._count(2)
+            _cabi.check(self._lib.mvoc_exchange_allgather(t.data_ptr(), nbytes, self.peer_bases, off, self.rank, P,
+                                                          site | self._flag, self._stream()), "mvoc_exchange_allgather")
+            self._wait(site)
         return out
 
     def close(self) -> None:

@@ -16,6 +16,7 @@ for what in "$@"; do
     case "$what" in
         check)   run 240 "mg_check" $TR --master-port 29521 tools/multigpu_check.py config2 2 ;;
         config2) run 240 "bench_config2" $TR --master-port 29522 bench.py --gpus $N --steps 10 --warmup 3 ;;
+        sepwait) MVOC_EXCHANGE_WAIT=separate run 240 "bench_config2_sepwait" $TR --master-port 29528 bench.py --gpus $N --steps 10 --warmup 3 ;;
         nccl)    MVOC_EXCHANGE=nccl run 240 "bench_config2_nccl" $TR --master-port 29523 bench.py --gpus $N --steps 10 --warmup 3 ;;
         gather)  MVOC_FP_GATHER_MAX_PIXELS=256 run 240 "bench_config2_gather256" $TR --master-port 29524 bench.py --gpus $N --steps 10 --warmup 3 ;;
         config3) run 240 "bench_config3" $TR --master-port 29525 bench.py --gpus $N --workload config3 --steps 6 --warmup 3 ;;
