@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
-# Round-2 session O: validation of the GEMM epilogue rework (8 epilogue warps, tail tiles, grid-constant params).
+# GEMM session: gemm_check correctness (all sections, both CTA modes) + timings, isolated kernel timings, kernel tests, a short bench.
 set -u
-TAG="${1:-r02o}"
+TAG="${1:-r02k}"
 OUT=gpurun_out
 mkdir -p "$OUT"
 run() {
@@ -17,7 +17,7 @@ for v in 1 0; do
     done
 done
 run 150 gemm_time_v1 tools/gemm_check time 1
-run 100 gemm_short_v1 tools/gemm_check short 1
-run 700 pytest_gpu python -m pytest tests -m gpu -x -q
-run 200 bench_n1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline
+run 120 kernel_times python tools/gpu_diag.py time
+run 300 pytest_kernels python -m pytest tests/test_kernels_gpu.py tests/test_properties_gpu.py -m gpu -x -q
+run 200 bench_n1 python bench.py --steps 5 --warmup 3 --no-cpu-baseline
 echo "== done" | tee -a "$OUT/${TAG}_session.log"
