@@ -373,7 +373,9 @@ static int section_width(int variant) {
 
 // short-K Linears (HBM / epilogue bound): the same launch with parts of the kernel switched off (variant bits 20..23)
 static int section_short(int variant) {
-    const int64_t lins[][4] = {{327680, 320, 320, 0}, {327680, 320, 320, 1}, {327680, 320, 960, 0}, {81920, 640, 640, 1}};
+    // the last four are the per-rank shapes of an 8-GPU run (latency floor of a launch: one tile per CTA or fewer)
+    const int64_t lins[][4] = {{327680, 320, 320, 0}, {327680, 320, 320, 1}, {327680, 320, 960, 0}, {81920, 640, 640, 1},
+                               {2560, 1280, 1280, 0}, {2560, 1280, 1280, 1}, {640, 1280, 1280, 0}, {256, 64, 64, 0}};
     const int dbgs[] = {0, 3, 4, 7, 8, 11};
     for (auto& c : lins) {
         const int64_t M = c[0];
