@@ -211,14 +211,13 @@ int mvoc_groupnorm_silu(const void* x, void* y, const void* gamma, const void* b
  * sites as mvoc_groupnorm_silu, for the NHWC host path; `add` [N, C] (nullable) fuses the resnet's
  * `hidden_states + temb` (i2vgen-xl/pnp_utils.py:941-953) into the normalisation.
  * Three launches so that the statistics of pixel shards can be merged across GPUs in between:
- *   stats    -> partial [N, G, chunks] float2 (mean, M2); chunks from mvoc_groupnorm_nhwc_geometry (it depends
- *               on N as well: tensors of few frames are cut into more chunks so that every SM gets work)
+ *   stats    -> partial [N, G, chunks] float2 (mean, M2); chunks from mvoc_groupnorm_nhwc_geometry
  *   finalize -> stat [N / frames_per_stat, G] float2 (mean, rstd); merges `sets` partial arrays laid out
  *               [sets, N, G, chunks] with element counts counts[sets, chunks] (float)
  *   apply    -> y = silu?((x + add - mean) * rstd * gamma + beta); y may alias x
  */
 int64_t mvoc_groupnorm_nhwc_partial_count(int64_t N, int G);
-int mvoc_groupnorm_nhwc_geometry(int64_t N, int64_t S, int C, int dtype, int* chunks, int64_t* tokens_per_chunk);
+int mvoc_groupnorm_nhwc_geometry(int64_t S, int C, int dtype, int* chunks, int64_t* tokens_per_chunk);
 int mvoc_groupnorm_nhwc_stats(const void* x, const void* add, void* partial, int64_t N, int64_t S, int C,
                               int G, int dtype, void* stream);
 int mvoc_groupnorm_nhwc_finalize(const void* partial, const void* counts, void* stat, int64_t N, int G,

@@ -48,7 +48,7 @@ SIGNATURES = {
     ),
     "mvoc_groupnorm_nhwc_partial_count": (c_int64, [c_int64, c_int]),
     "mvoc_groupnorm_nhwc_geometry": (
-        c_int, [c_int64, c_int64, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int64)]),
+        c_int, [c_int64, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int64)]),
     "mvoc_groupnorm_nhwc_stats": (
         c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p]),
     "mvoc_groupnorm_nhwc_finalize": (

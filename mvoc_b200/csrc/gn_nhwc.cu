@@ -231,7 +231,7 @@ __global__ void gnh_apply_kernel(GNHParams p) {
     }
 }
 
-static void gnh_geometry(int64_t N, int64_t S, int C, int esize, int* chunks, int64_t* tpc, int* R) {
+static void gnh_geometry(int64_t S, int C, int esize, int* chunks, int64_t* tpc, int* R) {
     const int VC = C / 8;
     int r = 320 / VC;
     if (r < 1) r = 1;
@@ -239,12 +239,6 @@ static void gnh_geometry(int64_t N, int64_t S, int C, int esize, int* chunks, in
     while (VC * r > 1024) --r;
     int64_t ch = (S * (int64_t)C * esize + 160 * 1024 - 1) / (160 * 1024);
     if (ch < 1) ch = 1;
-    // few frames (the per-rank shard of a multi-GPU run: N = 10 at 8 GPUs): 160 KB chunks would leave most SMs
-    // without a CTA and every launch latency-bound (21 us per stats launch measured on 26 MB tensors), so split
-    // further until ~4 CTAs per SM exist, but not below 16 KB of X per CTA
-    const int64_t want = (4 * (int64_t)num_sms() + (N > 0 ? N : 1) - 1) / (N > 0 ? N : 1);
-    const int64_t finest = (S * (int64_t)C * esize) / (16 * 1024);
-    if (want > ch) ch = want < finest ? want : (finest > ch ? finest : ch);
     if (ch > GNH_MAX_CHUNKS) ch = GNH_MAX_CHUNKS;
     int64_t t = (S + ch - 1) / ch;
     *chunks = (int)((S + t - 1) / t);
@@ -282,12 +276,12 @@ extern "C" int64_t mvoc_groupnorm_nhwc_partial_count(int64_t N, int G) {
     return N * (int64_t)G * GNH_MAX_CHUNKS;
 }
 
-extern "C" int mvoc_groupnorm_nhwc_geometry(int64_t N, int64_t S, int C, int dtype, int* chunks,
+extern "C" int mvoc_groupnorm_nhwc_geometry(int64_t S, int C, int dtype, int* chunks,
                                             int64_t* tokens_per_chunk) {
     MVOC_REQUIRE(S > 0 && C > 0 && C % 8 == 0, MVOC_ERR_UNSUPPORTED,
                  "mvoc_groupnorm_nhwc_geometry: need S>0 and C%%8==0 (S=%lld C=%d)", (long long)S, C);
     int R;
-    gnh_geometry(N, S, C, dtype == MVOC_F32 ? 4 : 2, chunks, tokens_per_chunk, &R);
+    gnh_geometry(S, C, dtype == MVOC_F32 ? 4 : 2, chunks, tokens_per_chunk, &R);
     return MVOC_OK;
 }
 
@@ -316,7 +310,7 @@ extern "C" int mvoc_groupnorm_nhwc_stats(const void* x, const void* add, void* p
     p.S = S;
     p.C = C;
     p.G = G;
-    gnh_geometry(N, S, C, 2, &p.chunks, &p.tokens_per_chunk, &p.R);
+    gnh_geometry(S, C, 2, &p.chunks, &p.tokens_per_chunk, &p.R);
     const int threads = (C / 8) * p.R;
     MVOC_REQUIRE(threads >= G, MVOC_ERR_UNSUPPORTED, "mvoc_groupnorm_nhwc_stats: C=%d too small for G=%d", C, G);
     dim3 grid(p.chunks, (unsigned)N);
@@ -367,7 +361,7 @@ extern "C" int mvoc_groupnorm_nhwc_apply(const void* x, void* y, const void* gam
     p.G = G;
     p.frames = frames_per_stat;
     p.silu = silu;
-    gnh_geometry(N, S, C, 2, &p.chunks, &p.tokens_per_chunk, &p.R);
+    gnh_geometry(S, C, 2, &p.chunks, &p.tokens_per_chunk, &p.R);
     const int threads = (C / 8) * p.R;
     dim3 grid(p.chunks, (unsigned)N);
     cudaStream_t st = (cudaStream_t)stream;

@@ -416,14 +416,14 @@ _gnh_geom: dict = {}
 _gnh_bufs: dict = {}
 
 
-def _gnh_geometry(N: int, S: int, C: int, dt: int):
-    key = (N, S, C, dt)
+def _gnh_geometry(S: int, C: int, dt: int):
+    key = (S, C, dt)
     g = _gnh_geom.get(key)
     if g is None:
         import ctypes
 
         chunks, tpc = ctypes.c_int(0), ctypes.c_int64(0)
-        _cabi.check(_cabi.load().mvoc_groupnorm_nhwc_geometry(N, S, C, dt, ctypes.byref(chunks), ctypes.byref(tpc)),
+        _cabi.check(_cabi.load().mvoc_groupnorm_nhwc_geometry(S, C, dt, ctypes.byref(chunks), ctypes.byref(tpc)),
                     "mvoc_groupnorm_nhwc_geometry")
         g = (chunks.value, tpc.value)
         _gnh_geom[key] = g
@@ -456,7 +456,7 @@ def _groupnorm_nhwc_slab(
         raise ValueError(f"groupnorm_nhwc: add must be contiguous [{N}, {C}] of x's dtype")
     dt = _dt(x)
     lib = _cabi.load()
-    chunks, tpc = _gnh_geometry(N, S, C, dt)
+    chunks, tpc = _gnh_geometry(S, C, dt)
     partial = torch.empty((N, groups, chunks, 2), dtype=torch.float32, device=x.device)
     with _Timed(("groupnorm", N, C, S, frames_per_stat), 2.0 * x.numel() * x.element_size()):
         _cabi.check(lib.mvoc_groupnorm_nhwc_stats(x.data_ptr(), _ptr(add), partial.data_ptr(), N, S, C, groups, dt,
@@ -465,7 +465,7 @@ def _groupnorm_nhwc_slab(
         if gather is not None:
             partial = gather(partial)
             sets = partial.shape[0]
-        ckey = (x.device.index, N, S, C, groups, sets)
+        ckey = (x.device.index, S, C, groups, sets)
         counts = _gnh_bufs.get(ckey)
         if counts is None:
             cg = C // groups

@@ -385,7 +385,7 @@ def test_groupnorm_nhwc_sharded_statistics(cuda_device):
 
     lib = _cabi.load()
     parts = []
-    chunks, _ = ops._gnh_geometry(N, S // P, C, 0)
+    chunks, _ = ops._gnh_geometry(S // P, C, 0)
     for sh in shards:
         part = torch.empty(N, 32, chunks, 2, device=cuda_device)
         _cabi.check(lib.mvoc_groupnorm_nhwc_stats(sh.data_ptr(), None, part.data_ptr(), N, S // P, C, 32, 0, None), "stats")
