@@ -459,6 +459,22 @@ def run_mvoc(args):
         "exchange_calls_per_step": (sum(summ[k][0] for k in ex_keys) / K) if ex_keys else None,
     }
 
+    # the kernel the step spends most of its time in since round 2: the tcgen05 GEMM family (same roofline fields)
+    roof_dense = None
+    if gemm_keys and gemm_ms > 0:
+        g_ach = sum(summ[k][2] for k in gemm_keys) / (gemm_ms / 1e3) / 1e12
+        roof_dense = {
+            "bound": "tensor", "kernel": "gemm_tc_kernel: every 3x3 conv, temporal conv, Linear and GEGLU projection of the step "
+                                         "(short-K Linears included, which are epilogue / HBM bound)",
+            "achieved": g_ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+            "frac": g_ach / peaks["bf16_tflops_sustained"], "flops": "2*rows*N*K_total per launch",
+            "launches": sum(summ[k][0] for k in gemm_keys), "share_of_step": gemm_ms / ms_total,
+            "conv3x3_only": {"achieved": extra["conv3x3_tflops"],
+                             "frac": (extra["conv3x3_tflops"] / peaks["bf16_tflops_sustained"])
+                             if extra["conv3x3_tflops"] else None},
+            "traffic": None, "traffic_source": "per-shape ncu captures: profiles/r02_final_ncu_*_summary.txt (DRAM bytes = algorithmic)",
+        }
+
     # where the (eager-replayed) step goes: the twelve heaviest timer keys, work in TFLOP/s or GB/s by kernel family
     tops = sorted(summ.items(), key=lambda kv: -kv[1][1])[:12]
     extra["top"] = [{"key": "/".join(str(x) for x in k), "calls_per_step": n / K, "ms_per_step": ms / K,
@@ -495,6 +511,7 @@ def run_mvoc(args):
                          if os.environ.get(k)},
         },
         "roofline": roof,
+        "roofline_dense": roof_dense,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms_step, "matches_device_resident_run": same},
