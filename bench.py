@@ -506,7 +506,7 @@ def run_mvoc(args):
             "cuda_graphs": bool(pipe.use_cuda_graphs),
             "eager_ms_per_step": ms_eager_total / K,
             # experiment switches (all off for the product numbers; a line with any of them set is an A/B line)
-            "switches": {k: os.environ[k] for k in ("MVOC_DENSE", "MVOC_GEMM_VARIANT", "MVOC_EXCHANGE", "MVOC_EXCHANGE_WAIT", "MVOC_GN_SLAB_MB",
+            "switches": {k: os.environ[k] for k in ("MVOC_DENSE", "MVOC_GEMM_VARIANT", "MVOC_EXCHANGE", "MVOC_EXCHANGE_WAIT",
                                                               "MVOC_FP_GATHER_MAX_PIXELS")
                          if os.environ.get(k)},
         },

@@ -483,12 +483,6 @@ def _groupnorm_nhwc_slab(
     return out
 
 
-# MVOC_GN_SLAB_MB=<n> (off by default, unmeasured): run the three GroupNorm launches slab by slab, n MB of
-# statistic groups at a time, so that the `apply` pass re-reads a slab that the `stats` pass has just pulled into
-# the 126 MB L2 — two DRAM passes over the tensor instead of three.
-_GN_SLAB_BYTES = int(float(os.environ.get("MVOC_GN_SLAB_MB", "0") or 0) * (1 << 20))
-
-
 def groupnorm_nhwc(
     x: torch.Tensor,
     weight: torch.Tensor,
@@ -502,18 +496,6 @@ def groupnorm_nhwc(
     gather=None,
 ) -> torch.Tensor:
     """GroupNorm(+SiLU) over channels-last x [N, S, C] (or [N, H, W, C]); see _groupnorm_nhwc_slab."""
-    N = x.shape[0]
-    if _GN_SLAB_BYTES > 0 and gather is None and N > frames_per_stat and x.is_contiguous():
-        group_bytes = frames_per_stat * (x.numel() // N) * x.element_size()    # one statistics group
-        step = max(1, _GN_SLAB_BYTES // group_bytes) * frames_per_stat
-        if step < N:
-            if out is None:
-                out = torch.empty_like(x)
-            for n0 in range(0, N, step):
-                n1 = min(N, n0 + step)
-                _groupnorm_nhwc_slab(x[n0:n1], weight, bias, groups, eps, silu, frames_per_stat,
-                                     None if add is None else add[n0:n1], out[n0:n1], None)
-            return out
     return _groupnorm_nhwc_slab(x, weight, bias, groups, eps, silu, frames_per_stat, add, out, gather)
 
 

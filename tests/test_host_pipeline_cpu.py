@@ -263,29 +263,6 @@ def test_derived_weights_follow_load_state_dict(emulated_ops):
     assert torch.allclose(attn.qkv_self(x)[0], q0, atol=1e-5)
 
 
-def test_host_groupnorm_slabs_vs_oracle(emulated_ops, monkeypatch):
-    """MVOC_GN_SLAB_MB: GroupNorm issued slab by slab (whole statistic groups per slab, in-place and fused-add
-    variants included) gives the same composition result."""
-    from mvoc_b200 import ops
-    from oracle import pipeline as opipe
-
-    slabs = []
-    real = ops._groupnorm_nhwc_slab
-
-    def spy(x, *a, **k):
-        slabs.append(x.shape[0])
-        return real(x, *a, **k)
-
-    monkeypatch.setattr(ops, "_groupnorm_nhwc_slab", spy)
-    monkeypatch.setattr(ops, "_GN_SLAB_BYTES", 96 * 1024)      # a few frames of the reduced model per slab
-    wl, sched, inputs, ou = _setup("reduced2")
-    ref = opipe.composite_loop(copy.deepcopy(ou), wl, inputs, max_steps=1)
-    out = _composite(wl, sched, inputs, _product_cpu(ou, wl.unet), 1)
-    assert rel_l2(out, ref) <= TOL
-    full = wl.n_branches * wl.n_frames
-    assert any(n < full for n in slabs), "no call was split into slabs"
-
-
 # ------------------------------------------------------------------ the reference's own step loops (golden)
 @pytest.mark.parametrize("case", ["default", "exotic"])
 def test_host_composition_loop_vs_reference_golden(emulated_ops, case):
