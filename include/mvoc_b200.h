@@ -265,6 +265,14 @@ int mvoc_upsample_nearest2x_nhwc(const void* x, void* y, int64_t N, int H, int W
  * Replaces conv1 / conv2 / conv_shortcut + the skip add of the resnet closure, i2vgen-xl/pnp_utils.py:939,
  * :968, :1011-1018, and the same calls inside diffusers' stock ResnetBlock2D / Upsample2D.
  */
+/*
+ * Host-side tile plan of the GEMM kernel for `rows` output rows x N output columns on a chip of `sms` SMs (no device
+ * call; `variant` as in the compute entries): the column-tile width, whether CTA pairs are used, and the width of
+ * the narrower last column tile (0 = the width divides N).  What the compute entries choose internally.
+ */
+int mvoc_gemm_plan(int64_t rows, int64_t N, int geglu, int variant, int sms, int* tile_cols, int* cta_pair,
+                   int* tail_cols);
+
 int mvoc_conv3x3_nhwc(const void* x, const void* w_taps, const void* bias, const void* residual,
                       const void* x2, const void* w2, int Cin2, void* out,
                       int N, int H, int W, int Cin, int Cout, int dtype, int variant, void* stream);

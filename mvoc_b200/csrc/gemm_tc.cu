@@ -772,6 +772,45 @@ static int launch_bn(const Problem& pb, const Params& prm, int b1, int b2, int b
     return launch_cfg<Cfg<BN, false, kEpi>, __nv_bfloat16>(pb, prm, b1, b2, b3, s);
 }
 
+// Tile width (0 = none fits) and CTA mode for a problem of m_tiles 128-row tiles x N output columns on a chip of `sms`
+// SMs: the cheapest of waves x chunk cost over the available widths.  variant bit 0 allows CTA pairs, bit 1 forbids a
+// narrower tail tile, bits 8.. force a width.  Also exported as mvoc_gemm_plan (host logic, testable without a GPU).
+static void plan_tiles(int64_t m_tiles, int64_t N, bool geglu, int variant, int sms, int* bn_out, bool* pair_out) {
+    const int forced = (variant >> 8) & 0x1ff;
+    const bool allow_pair = (variant & 1) != 0;
+    const int widths_lin[5] = {256, 192, 160, 128, 64};
+    const int widths_geglu[2] = {256, 128};
+    const int* widths = geglu ? widths_geglu : widths_lin;
+    const int n_widths = geglu ? 2 : 5;
+    const bool allow_tail = (variant & 2) == 0;   // variant bit 1: only widths that divide N (A/B switch)
+    int BN = 0;
+    bool two = false;
+    double best = 0.0;
+    for (int i = 0; i < n_widths; ++i) {
+        const int w = widths[i];
+        const int out_cols = geglu ? w / 2 : w;
+        if (forced && forced != w) continue;
+        // a narrower LAST column tile (multiple of 64 columns) lets 256-wide tiles cover N = 640, 1920, 320 ...
+        const int tail = (int)(N % out_cols);
+        if (tail != 0 && (geglu || !allow_tail || w % 64 != 0 || tail % 64 != 0)) continue;
+        const int64_t n_full = N / out_cols;
+        const int64_t n_tiles = n_full + (tail ? 1 : 0);
+        for (int pair = allow_pair ? 1 : 0; pair >= 0; --pair) {
+            const int64_t units = (pair ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
+            const int64_t slots = pair ? sms / 2 : sms;
+            const double waves = (double)((units + slots - 1) / slots);
+            // a pair tile covers two row tiles; the tail tile still fills a full-width weight box
+            const double per_tile = ((double)n_full * chunk_cost(w, pair != 0) +
+                                     (tail ? 0.5 * (chunk_cost(tail, pair != 0) + chunk_cost(w, pair != 0)) : 0.0)) /
+                                    (double)n_tiles;
+            const double cost = waves * per_tile;
+            if (BN == 0 || cost < best * 0.999) best = cost, BN = w, two = pair != 0;
+        }
+    }
+    *bn_out = BN;
+    *pair_out = two;
+}
+
 static int run(const Problem& pb, cudaStream_t stream) {
     const char* what = pb.what;
     MVOC_REQUIRE(pb.dtype == MVOC_BF16 || pb.dtype == MVOC_F16, MVOC_ERR_UNSUPPORTED,
@@ -812,39 +851,11 @@ static int run(const Problem& pb, cudaStream_t stream) {
     // has SMs (the low-resolution levels, and every level once the frames are sharded over 8 GPUs), where narrower
     // tiles and single CTAs fill more SMs.  Pick the cheapest of
     // waves x chunk cost; variant bit 0 allows CTA pairs, bit 1 forbids a narrower tail tile, bits 8.. force a width.
-    const int forced = (pb.variant >> 8) & 0x1ff;
-    const bool allow_pair = (pb.variant & 1) != 0;
     const int64_t m_tiles = (int64_t)prm.t1 * prm.t2 * ((pb.d3 + b3 - 1) / b3);
-    const int sms = num_sms();
-    const int widths_lin[5] = {256, 192, 160, 128, 64};
-    const int widths_geglu[2] = {256, 128};
-    const int* widths = pb.geglu ? widths_geglu : widths_lin;
-    const int n_widths = pb.geglu ? 2 : 5;
-    const bool allow_tail = (pb.variant & 2) == 0;   // variant bit 1: only widths that divide N (A/B switch)
+    const int forced = (pb.variant >> 8) & 0x1ff;
     int BN = 0;
     bool two = false;
-    double best = 0.0;
-    for (int i = 0; i < n_widths; ++i) {
-        const int w = widths[i];
-        const int out_cols = pb.geglu ? w / 2 : w;
-        if (forced && forced != w) continue;
-        // a narrower LAST column tile (multiple of 64 columns) lets 256-wide tiles cover N = 640, 1920, 320 ...
-        const int tail = (int)(pb.N % out_cols);
-        if (tail != 0 && (pb.geglu || !allow_tail || w % 64 != 0 || tail % 64 != 0)) continue;
-        const int64_t n_full = pb.N / out_cols;
-        const int64_t n_tiles = n_full + (tail ? 1 : 0);
-        for (int pair = allow_pair ? 1 : 0; pair >= 0; --pair) {
-            const int64_t units = (pair ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
-            const int64_t slots = pair ? sms / 2 : sms;
-            const double waves = (double)((units + slots - 1) / slots);
-            // a pair tile covers two row tiles; the tail tile still fills a full-width weight box
-            const double per_tile = ((double)n_full * chunk_cost(w, pair != 0) +
-                                     (tail ? 0.5 * (chunk_cost(tail, pair != 0) + chunk_cost(w, pair != 0)) : 0.0)) /
-                                    (double)n_tiles;
-            const double cost = waves * per_tile;
-            if (BN == 0 || cost < best * 0.999) best = cost, BN = w, two = pair != 0;
-        }
-    }
+    plan_tiles(m_tiles, pb.N, pb.geglu != 0, pb.variant, num_sms(), &BN, &two);
     MVOC_REQUIRE(BN != 0, MVOC_ERR_UNSUPPORTED, "%s: no tile width (forced %d) divides N=%lld", what, forced,
                  (long long)pb.N);
     if (pb.geglu) {
@@ -867,6 +878,21 @@ static int run(const Problem& pb, cudaStream_t stream) {
 }  // namespace mvoc
 
 using namespace mvoc;
+
+extern "C" int mvoc_gemm_plan(int64_t rows, int64_t N, int geglu, int variant, int sms, int* tile_cols, int* cta_pair,
+                              int* tail_cols) {
+    MVOC_REQUIRE(tile_cols && cta_pair && tail_cols, MVOC_ERR_INVALID_ARG, "mvoc_gemm_plan: null pointer");
+    MVOC_REQUIRE(rows > 0 && N > 0 && N % 64 == 0 && sms >= 2, MVOC_ERR_INVALID_ARG,
+                 "mvoc_gemm_plan: rows=%lld N=%lld (a multiple of 64) sms=%d", (long long)rows, (long long)N, sms);
+    int bn = 0;
+    bool pair = false;
+    gemm::plan_tiles((rows + gemm::BM - 1) / gemm::BM, N, geglu != 0, variant, sms, &bn, &pair);
+    MVOC_REQUIRE(bn != 0, MVOC_ERR_UNSUPPORTED, "mvoc_gemm_plan: no tile width tiles N=%lld", (long long)N);
+    *tile_cols = bn;
+    *cta_pair = pair ? 1 : 0;
+    *tail_cols = (int)(N % (geglu ? bn / 2 : bn));
+    return MVOC_OK;
+}
 
 extern "C" int mvoc_conv3x3_nhwc(const void* x, const void* w_taps, const void* bias, const void* residual,
                                  const void* x2, const void* w2, int Cin2, void* out, int N, int H, int W, int Cin,

@@ -75,6 +75,39 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert rc == -1 and b"null pointer" in lib.mvoc_last_error()
 
 
+def test_gemm_tile_plan_host_logic():
+    """mvoc_gemm_plan (no device call): what the GEMM entries choose.  On B200 a tcgen05.mma costs the same whatever
+    N <= 256 is, so the plan minimises the NUMBER of column tiles: full 256-wide tiles plus one narrower tail tile;
+    problems with fewer tiles than SMs get narrower tiles instead."""
+    import ctypes
+
+    from mvoc_b200 import _cabi
+
+    lib = _cabi.load()
+
+    def plan(rows, N, geglu=0, variant=1, sms=148):
+        bn, pair, tail = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        rc = lib.mvoc_gemm_plan(rows, N, geglu, variant, sms, ctypes.byref(bn), ctypes.byref(pair), ctypes.byref(tail))
+        return rc, bn.value, pair.value, tail.value
+
+    for rows in (327680, 81920, 20480):                      # config 2's levels 0-2 on one GPU
+        assert plan(rows, 640) == (0, 256, 1, 128)           # 256 + 256 + 128, not 4 x 160
+        assert plan(rows, 960) == (0, 256, 1, 192)
+        assert plan(rows, 1920) == (0, 256, 1, 128)
+        assert plan(rows, 1280) == (0, 256, 1, 0)
+        rc, bn, pair, tail = plan(rows, 320)                 # two column tiles whichever way
+        assert rc == 0 and pair == 1 and (tail == 320 - bn or (bn == 160 and tail == 0))
+    assert plan(81920, 640, variant=3) == (0, 160, 1, 0)     # bit 1: only widths that divide N
+    assert plan(81920, 640, variant=0)[2] == 0               # bit 0 clear: no CTA pairs
+    assert plan(81920, 640, variant=1 | (192 << 8)) == (0, 192, 1, 64)   # forced width, tail covers the rest
+    assert plan(327680, 1280, geglu=1) == (0, 256, 1, 0)     # GEGLU: value + gate columns share one 256-wide tile
+    # the per-rank shapes of an 8-GPU run have fewer row tiles than the chip has SMs: narrower tiles fill more of them
+    assert plan(640, 1280)[1] == 64 and plan(2560, 320)[1] == 64
+    assert plan(640, 1280, sms=16)[1] == 256                 # ... unless the chip is small
+    rc = plan(100, 100)[0]
+    assert rc == -1 and b"multiple of 64" in lib.mvoc_last_error()
+
+
 def test_product_ops_refuse_cpu_tensors():
     """No CPU fallback: the product raises instead of computing with torch."""
     from mvoc_b200 import ops
